@@ -1,0 +1,268 @@
+// pcr_capi.cu — extern "C" entry points declared in include/pcr.h and the end-to-end align driver.
+#include "pcr_common.cuh"
+
+typedef unsigned long long u64;
+
+// implementation functions (one per translation unit)
+int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, const float4 *nrm, int nt,
+                 double max_dist, const double *init, int max_iter, double rel_fit, double rel_rmse,
+                 pcr_reg_result *res, int *corr, bool sync_result);
+int pcr_nn1_impl(pcr_ctx *ctx, const float4 *tgt, int nt, const float4 *q, int nq, double radius, int *idx, float *d2);
+int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq, double radius, int max_nn, int *idx,
+                 float *d2, int *cnt);
+int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int max_nn, float4 *normals);
+int pcr_fpfh_impl(pcr_ctx *ctx, const float4 *pts, const float4 *nrm, int n, double radius, int max_nn, float *out);
+int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, int *m_host);
+int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn);
+int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int mt, int mutual, double mutual_ratio,
+                   int *corr, int *c_host);
+int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, const int *corr, int c,
+                    double max_dist, double edge_sim, int64_t max_iter, double confidence, u64 seed,
+                    pcr_reg_result *res);
+struct RansacWork {
+    Grid g;
+    const float4 *src_sorted;
+    float r2;
+    int k_d;
+};
+int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist,
+                       RansacWork *w);
+int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt,
+                         const int *corr, int c, double max_dist, double edge_sim, long long hyp_begin,
+                         long long hyp_end, u64 seed, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
+                         int cap, int *n_recs_host, long long *n_surv_host);
+int pcr_ransac_step_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, u64 seed,
+                         long long h_begin, int count, double *T);
+int pcr_inlier_count_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, const double *T,
+                          int count, double thresh, int squared, int *counts);
+
+int pcr_pack_impl(pcr_ctx *ctx, const float *xyz, int n, float4 *out);
+
+struct CallGuard {
+    pcr_ctx *ctx;
+    bool ok;
+    explicit CallGuard(pcr_ctx *c) : ctx(c), ok(false) {
+        if (!ctx || ctx->busy) return;
+        ctx->busy = true;
+        ok = true;
+        cudaSetDevice(ctx->device);
+        pcr_arena_reset(ctx);
+    }
+    ~CallGuard() {
+        if (ok) ctx->busy = false;
+    }
+};
+#define PCR_ENTER()                   \
+    if (!ctx) return PCR_ERR_INVALID; \
+    CallGuard guard__(ctx);           \
+    if (!guard__.ok) return pcr_fail(ctx, PCR_ERR_BUSY, "context is in use by another call")
+#define PCR_ARG(cond) \
+    if (!(cond)) return pcr_fail(ctx, PCR_ERR_INVALID, "invalid argument: %s", #cond)
+
+extern "C" {
+
+int pcr_voxel_downsample(pcr_ctx *ctx, const float *xyzw, int n, double voxel, float *out, int *m_host) {
+    PCR_ENTER();
+    PCR_ARG(n >= 0 && m_host);
+    return pcr_voxel_impl(ctx, (const float4 *)xyzw, n, voxel, (float4 *)out, m_host);
+}
+
+int pcr_estimate_normals(pcr_ctx *ctx, const float *xyzw, int n, double radius, int max_nn, float *normals) {
+    PCR_ENTER();
+    PCR_ARG(n >= 0);
+    return pcr_normals_impl(ctx, (const float4 *)xyzw, n, radius, max_nn, (float4 *)normals);
+}
+
+int pcr_compute_fpfh(pcr_ctx *ctx, const float *xyzw, const float *normals, int n, double radius, int max_nn,
+                     float *fpfh) {
+    PCR_ENTER();
+    PCR_ARG(n >= 0);
+    return pcr_fpfh_impl(ctx, (const float4 *)xyzw, (const float4 *)normals, n, radius, max_nn, fpfh);
+}
+
+int pcr_knn_hybrid(pcr_ctx *ctx, const float *xyzw, int n, const float *q, int nq, double radius, int max_nn, int *idx,
+                   float *d2, int *cnt) {
+    PCR_ENTER();
+    PCR_ARG(n >= 0 && nq >= 0);
+    return pcr_knn_impl(ctx, (const float4 *)xyzw, n, (const float4 *)q, nq, radius, max_nn, idx, d2, cnt);
+}
+
+int pcr_nn1(pcr_ctx *ctx, const float *tgt, int nt, const float *q, int nq, double radius, int *idx, float *d2) {
+    PCR_ENTER();
+    PCR_ARG(nt >= 0 && nq >= 0);
+    return pcr_nn1_impl(ctx, (const float4 *)tgt, nt, (const float4 *)q, nq, radius, idx, d2);
+}
+
+int pcr_match_features(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int mt, int mutual, double mutual_ratio,
+                       int *corr, int *c_host) {
+    PCR_ENTER();
+    PCR_ARG(ms >= 0 && mt >= 0 && c_host);
+    return pcr_match_impl(ctx, fs, ms, ft, mt, mutual, mutual_ratio, corr, c_host);
+}
+
+int pcr_nn_features(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn) {
+    PCR_ENTER();
+    PCR_ARG(nq >= 0 && nb >= 0);
+    return pcr_nn_features_impl(ctx, fq, nq, fb, nb, nn);
+}
+
+int pcr_ransac(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt, const int *corr, int c,
+               double max_dist, double edge_sim, int64_t max_iter, double confidence, uint64_t seed,
+               pcr_reg_result *result) {
+    PCR_ENTER();
+    PCR_ARG(ms >= 0 && mt >= 0 && c >= 0 && result);
+    return pcr_ransac_impl(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, corr, c, max_dist, edge_sim, max_iter,
+                           confidence, seed, result);
+}
+
+int pcr_ransac_wave(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt, const int *corr, int c,
+                    double max_dist, double edge_sim, int64_t hyp_begin, int64_t hyp_end, uint64_t seed,
+                    int64_t best_count, int64_t best_sum, pcr_hyp_record *records, int cap, int *n_records,
+                    int64_t *n_survivors) {
+    PCR_ENTER();
+    PCR_ARG(ms > 0 && mt > 0 && c >= 3 && max_dist > 0.0 && records && cap > 0 && n_records && n_survivors);
+    RansacWork w;
+    PCR_TRY(pcr_ransac_prepare(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, max_dist, &w));
+    long long ns = 0;
+    const int rc = pcr_ransac_wave_impl(ctx, w, (const float4 *)src, ms, (const float4 *)tgt, corr, c, max_dist, edge_sim,
+                                        hyp_begin, hyp_end, seed, best_count, best_sum, records, cap, n_records, &ns);
+    *n_survivors = ns;
+    return rc;
+}
+
+int pcr_ransac_step(pcr_ctx *ctx, const float *src, const float *tgt, const int *corr, int c, uint64_t seed,
+                    int64_t h_begin, int count, double *T) {
+    PCR_ENTER();
+    PCR_ARG(c >= 0 && count >= 0);
+    return pcr_ransac_step_impl(ctx, (const float4 *)src, (const float4 *)tgt, corr, c, seed, h_begin, count, T);
+}
+
+int pcr_inlier_count(pcr_ctx *ctx, const float *src, const float *tgt, const int *corr, int c, const double *T,
+                     int count, double thresh, int squared, int *counts) {
+    PCR_ENTER();
+    PCR_ARG(c >= 0 && count >= 0);
+    return pcr_inlier_count_impl(ctx, (const float4 *)src, (const float4 *)tgt, corr, c, T, count, thresh, squared,
+                                 counts);
+}
+
+int pcr_icp_point_to_plane(pcr_ctx *ctx, const float *src, int ns, const float *tgt, const float *nrm, int nt,
+                           double max_dist, const double *init, int max_iter, double rel_fitness, double rel_rmse,
+                           pcr_reg_result *result, int *corr) {
+    PCR_ENTER();
+    PCR_ARG(ns >= 0 && nt >= 0 && init && result);
+    return pcr_icp_impl(ctx, (const float4 *)src, ns, (const float4 *)tgt, (const float4 *)nrm, nt, max_dist, init,
+                        max_iter, rel_fitness, rel_rmse, result, corr, true);
+}
+
+void pcr_align_default_params(pcr_align_params *p) {
+    if (!p) return;
+    p->voxel_size = 0.3;            // Ply default, src/ply/ply.py:32
+    p->ransac_max_iter = 30;        // src/matcher/ransac.py:24
+    p->ransac_confidence = 0.999;   // src/matcher/ransac.py:58
+    p->seed = 0;
+    p->icp_max_iter = 30;           // Open3D ICPConvergenceCriteria default (A.7)
+    p->icp_rel_fitness = 1e-6;
+    p->icp_rel_rmse = 1e-6;
+    p->source_normals = 1;          // Ply.__init__ estimates full-resolution normals on every cloud (ply.py:65)
+    p->reserved = 0;
+}
+
+}  // extern "C"
+
+// ---- end to end --------------------------------------------------------------------------------------------------
+struct StageTimer {
+    cudaEvent_t ev[9];
+    int n = 0;
+    cudaStream_t s;
+    explicit StageTimer(cudaStream_t st) : s(st) {
+        for (auto &e : ev) cudaEventCreate(&e);
+    }
+    ~StageTimer() {
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    void mark() {
+        if (n < 9) cudaEventRecord(ev[n++], s);
+    }
+};
+
+static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, const pcr_align_params *p,
+                        pcr_align_result *res) {
+    memset(res, 0, sizeof(*res));
+    const double v = p->voxel_size;
+    if (!(v > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "voxel_size must be > 0");
+    if (ns <= 0 || nt <= 0) return pcr_fail(ctx, PCR_ERR_INVALID, "Point cloud is empty");  // src/ply/ply.py:81-84
+    StageTimer tm(ctx->stream);
+    tm.mark();
+    // Ply._preprocess for both clouds (src/ply/ply.py:106-120)
+    PCR_ALLOC(sd, float4, (size_t)ns);
+    PCR_ALLOC(td, float4, (size_t)nt);
+    int ms = 0, mt = 0;
+    PCR_TRY(pcr_voxel_impl(ctx, src, ns, v, sd, &ms));
+    PCR_TRY(pcr_voxel_impl(ctx, tgt, nt, v, td, &mt));
+    tm.mark();
+    PCR_ALLOC(sn, float4, (size_t)ms);
+    PCR_ALLOC(tn, float4, (size_t)mt);
+    PCR_TRY(pcr_normals_impl(ctx, sd, ms, 2.0 * v, 30, sn));
+    PCR_TRY(pcr_normals_impl(ctx, td, mt, 2.0 * v, 30, tn));
+    tm.mark();
+    PCR_ALLOC(sf, float, (size_t)ms * 33);
+    PCR_ALLOC(tf, float, (size_t)mt * 33);
+    PCR_TRY(pcr_fpfh_impl(ctx, sd, sn, ms, 5.0 * v, 100, sf));
+    PCR_TRY(pcr_fpfh_impl(ctx, td, tn, mt, 5.0 * v, 100, tf));
+    tm.mark();
+    // global_registration (src/matcher/ransac.py:41-59): mutual filter True, threshold 1.5 v
+    PCR_ALLOC(corr, int, 2 * (size_t)ms);
+    int c = 0;
+    PCR_TRY(pcr_match_impl(ctx, sf, ms, tf, mt, 1, 0.1, corr, &c));
+    tm.mark();
+    PCR_TRY(pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed,
+                            &res->ransac));
+    tm.mark();
+    // Ply._add_normals on the full-resolution clouds (src/ply/ply.py:65,133-135)
+    PCR_ALLOC(tfn, float4, (size_t)nt);
+    PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, tfn));
+    if (p->source_normals) {
+        PCR_ALLOC(sfn, float4, (size_t)ns);
+        PCR_TRY(pcr_normals_impl(ctx, src, ns, 2.0 * v, 30, sfn));
+    }
+    tm.mark();
+    // refine_registration (src/matcher/icp.py:41-48): full-resolution clouds, threshold 0.4 v
+    PCR_TRY(pcr_icp_impl(ctx, src, ns, tgt, tfn, nt, 0.4 * v, res->ransac.transformation, p->icp_max_iter,
+                         p->icp_rel_fitness, p->icp_rel_rmse, &res->icp, nullptr, true));
+    tm.mark();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    res->n_src_down = ms;
+    res->n_tgt_down = mt;
+    res->n_corr = c;
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&res->stage_ms[i], tm.ev[i], tm.ev[i + 1]);
+    cudaEventElapsedTime(&res->stage_ms[7], tm.ev[0], tm.ev[7]);
+    return PCR_OK;
+}
+
+extern "C" {
+
+int pcr_align(pcr_ctx *ctx, const float *src, int ns, const float *tgt, int nt, const pcr_align_params *p,
+              pcr_align_result *result) {
+    PCR_ENTER();
+    PCR_ARG(p && result);
+    return align_device(ctx, (const float4 *)src, ns, (const float4 *)tgt, nt, p, result);
+}
+
+int pcr_align_host(pcr_ctx *ctx, const float *src_xyz, int ns, const float *tgt_xyz, int nt, const pcr_align_params *p,
+                   pcr_align_result *result) {
+    PCR_ENTER();
+    PCR_ARG(p && result && ns >= 0 && nt >= 0);
+    if (ns == 0 || nt == 0) return pcr_fail(ctx, PCR_ERR_INVALID, "Point cloud is empty");
+    PCR_ALLOC(s3, float, 3 * (size_t)ns);
+    PCR_ALLOC(t3, float, 3 * (size_t)nt);
+    PCR_ALLOC(s4, float4, (size_t)ns);
+    PCR_ALLOC(t4, float4, (size_t)nt);
+    PCR_CUDA(cudaMemcpyAsync(s3, src_xyz, sizeof(float) * 3 * (size_t)ns, cudaMemcpyHostToDevice, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(t3, tgt_xyz, sizeof(float) * 3 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    // pack without leaving the call (pcr_pack_xyz_f32 would re-enter the guard)
+    PCR_TRY(pcr_pack_impl(ctx, s3, ns, s4));
+    PCR_TRY(pcr_pack_impl(ctx, t3, nt, t4));
+    return align_device(ctx, s4, ns, t4, nt, p, result);
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// pcr_common.cuh — shared declarations of the B200 registration engine (sm_100a only).
+//
+// Arithmetic specification — every translation unit is compiled with -fmad=false so that
+// fp32/fp64 products and sums round exactly as the CPU oracle's; FMA is used only where written explicitly.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/pcr.h"
+#include "../../include/pcr_detmath.h"
+
+#define PCR_MAX_GRID_CELLS (1LL << 27)
+
+struct pcr_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // bump arena for per-call scratch (reset at the start of every exported call)
+    std::vector<void *> blocks;
+    std::vector<size_t> block_sizes;
+    size_t cur_block = 0, cur_off = 0;
+    // pinned host staging for small result records
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    bool busy = false;
+};
+
+extern std::atomic<long long> g_pcr_launches;
+#define PCR_LAUNCHED() (g_pcr_launches++)
+
+// ---- error handling -------------------------------------------------------------------------------
+int pcr_fail(pcr_ctx *ctx, int code, const char *fmt, ...);
+#define PCR_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return pcr_fail(ctx, PCR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define PCR_TRY(call)            \
+    do {                         \
+        int r__ = (call);        \
+        if (r__ != PCR_OK) return r__; \
+    } while (0)
+
+// ---- arena ----------------------------------------------------------------------------------------
+void pcr_arena_reset(pcr_ctx *ctx);
+void *pcr_arena_alloc(pcr_ctx *ctx, size_t bytes);  // 256-byte aligned; nullptr on failure (err set)
+template <typename T>
+static inline T *arena(pcr_ctx *ctx, size_t n) {
+    return reinterpret_cast<T *>(pcr_arena_alloc(ctx, n * sizeof(T)));
+}
+#define PCR_ALLOC(ptr, T, n)                                  \
+    T *ptr = arena<T>(ctx, (n));                              \
+    if (!ptr) return PCR_ERR_OOM
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- host-side spec helpers (restated independently in oracle/pcr_oracle.c) ---------------------------
+static inline int pcr_ilog2ceil(long long n) {
+    int e = 0;
+    while ((1LL << e) < n) e++;
+    return e;
+}
+int pcr_pow2ceil_exp(double x);  // smallest e with 2^e >= x
+
+// ---- uniform grid -----------------------------------------------------------------------------------
+// Dense grid over the bounding box of the indexed cloud; cells ordered x-fastest so that the three
+// x-neighbours of a cell are one contiguous range of the sorted point array.
+struct Grid {
+    const float4 *sorted;   // points sorted by cell; .w = original index (int bits)
+    const uint32_t *start;  // ncells+1 exclusive prefix
+    double ox, oy, oz;      // origin (min bound)
+    double inv_h;           // 1 / cell size
+    double h;
+    int nx, ny, nz;
+    int n;
+};
+
+// bounds: lo/hi (host) of a float4 cloud; one device reduction + one D2H sync
+int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]);
+// build a search grid supporting radius-`radius` queries with a 3x3x3 cell probe.
+// If bounds are already known pass them (have_bounds), else they are computed.
+int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo, const float *hi, Grid *g);
+// exclusive scan helpers (in pcr_grid.cu)
+int pcr_exclusive_scan_u32(pcr_ctx *ctx, uint32_t *data, long long n);  // in place, data[n] must exist (total)
+int pcr_exclusive_scan_u64(pcr_ctx *ctx, unsigned long long *data, long long n);
+
+// ---- device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // D1
+}
+
+// p' = fp32(R p + t), fp64 products/sums individually rounded (D7)
+__device__ __forceinline__ float3 xform_pt(const double *__restrict__ T, float x, float y, float z) {
+    const double dx = x, dy = y, dz = z;
+    float3 o;
+    o.x = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], dx), __dmul_rn(T[1], dy)), __dmul_rn(T[2], dz)), T[3]);
+    o.y = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], dx), __dmul_rn(T[5], dy)), __dmul_rn(T[6], dz)), T[7]);
+    o.z = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], dx), __dmul_rn(T[9], dy)), __dmul_rn(T[10], dz)), T[11]);
+    return o;
+}
+
+// cell coordinate in fp64 (exact to ~1e-13 cells; the cell size carries a 2^-10 margin over the radius so a
+// point with fp32 d2 < r2 is always within one cell of the query).  Clamped to [-2, n+1] before the int cast.
+__device__ __forceinline__ int grid_cell(double v, double o, double inv_h, int n) {
+    double c = floor((v - o) * inv_h);
+    c = fmin(fmax(c, -2.0), (double)n + 1.0);
+    return (int)c;
+}
+
+// radius-limited 1-NN in a grid: best (d2, idx) under the (d2, idx) lexicographic order, d2 < r2 strictly.
+// Returns original index or -1.
+__device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
+    const int cx = grid_cell((double)qx, g.ox, g.inv_h, g.nx);
+    const int cy = grid_cell((double)qy, g.oy, g.inv_h, g.ny);
+    const int cz = grid_cell((double)qz, g.oz, g.inv_h, g.nz);
+    float best = r2;
+    int bidx = -1;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    if (x0 <= x1) {
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+        for (int z = z0; z <= z1; z++) {
+            for (int y = y0; y <= y1; y++) {
+                const long long row = ((long long)z * g.ny + y) * g.nx;
+                const uint32_t b = __ldg(g.start + row + x0);
+                const uint32_t e = __ldg(g.start + row + x1 + 1);
+                for (uint32_t k = b; k < e; k++) {
+                    const float4 p = __ldg(g.sorted + k);
+                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    const int idx = __float_as_int(p.w);
+                    if (d2 < best || (d2 == best && bidx >= 0 && idx < bidx)) {
+                        best = d2;
+                        bidx = idx;
+                    }
+                }
+            }
+        }
+    }
+    *d2_out = best;
+    return bidx;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// llrint(x * 2^k): exact power-of-two scaling (scale = 2^k precomputed) then round-to-nearest-even (D5)
+__device__ __forceinline__ long long fixed_ll(double x, double scale) { return __double2ll_rn(__dmul_rn(x, scale)); }
+
+#endif  // __CUDACC__

@@ -1,0 +1,178 @@
+// pcr_ctx.cu — context, scratch arena, error plumbing, layout helpers.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "pcr_common.cuh"
+
+std::atomic<long long> g_pcr_launches{0};
+
+int pcr_fail(pcr_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int pcr_pow2ceil_exp(double x) {
+    int e;
+    const double m = frexp(x, &e);
+    return (m == 0.5) ? e - 1 : e;
+}
+
+void pcr_arena_reset(pcr_ctx *ctx) {
+    // keep only the largest block; free the rest so the arena converges to one block
+    if (ctx->blocks.size() > 1) {
+        size_t total = 0;
+        for (size_t s : ctx->block_sizes) total += s;
+        for (void *b : ctx->blocks) cudaFree(b);
+        ctx->blocks.clear();
+        ctx->block_sizes.clear();
+        void *p = nullptr;
+        if (cudaMalloc(&p, total) == cudaSuccess) {
+            ctx->blocks.push_back(p);
+            ctx->block_sizes.push_back(total);
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ctx->cur_block = 0;
+    ctx->cur_off = 0;
+}
+
+void *pcr_arena_alloc(pcr_ctx *ctx, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    while (ctx->cur_block < ctx->blocks.size()) {
+        if (ctx->cur_off + bytes <= ctx->block_sizes[ctx->cur_block]) {
+            void *p = (char *)ctx->blocks[ctx->cur_block] + ctx->cur_off;
+            ctx->cur_off += bytes;
+            return p;
+        }
+        ctx->cur_block++;
+        ctx->cur_off = 0;
+    }
+    size_t sz = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    void *p = nullptr;
+    // a fresh cudaMalloc is synchronous with respect to the device; it only happens while the arena warms up
+    if (cudaMalloc(&p, sz) != cudaSuccess) {
+        cudaGetLastError();
+        pcr_fail(ctx, PCR_ERR_OOM, "device allocation of %zu bytes failed", sz);
+        return nullptr;
+    }
+    ctx->blocks.push_back(p);
+    ctx->block_sizes.push_back(sz);
+    ctx->cur_block = ctx->blocks.size() - 1;
+    ctx->cur_off = bytes;
+    return p;
+}
+
+extern "C" {
+
+int pcr_version(void) { return 100; }
+
+int pcr_create(int device, pcr_ctx **out) {
+    if (!out) return PCR_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return PCR_ERR_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return PCR_ERR_CUDA;
+    pcr_ctx *ctx = new pcr_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete ctx;
+        return PCR_ERR_CUDA;  // sm_100a only: there is no fallback path
+    }
+    ctx->pinned_bytes = 1 << 20;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+        delete ctx;
+        return PCR_ERR_OOM;
+    }
+    *out = ctx;
+    return PCR_OK;
+}
+
+int pcr_destroy(pcr_ctx *ctx) {
+    if (!ctx) return PCR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *b : ctx->blocks) cudaFree(b);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+    return PCR_OK;
+}
+
+const char *pcr_last_error(pcr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pcr_set_stream(pcr_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return PCR_ERR_INVALID;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return PCR_OK;
+}
+
+int64_t pcr_launch_count(pcr_ctx *ctx) {
+    (void)ctx;
+    return g_pcr_launches.load();
+}
+
+}  // extern "C"
+
+// ---- layout helpers -----------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_xyz(const T *__restrict__ xyz, int n, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], 0.0f);
+}
+__global__ void k_unpack_xyz(const float4 *__restrict__ in, int n, float *__restrict__ xyz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float4 p = in[i];
+        xyz[3 * i] = p.x;
+        xyz[3 * i + 1] = p.y;
+        xyz[3 * i + 2] = p.z;
+    }
+}
+
+int pcr_pack_impl(pcr_ctx *ctx, const float *xyz, int n, float4 *out) {
+    if (n <= 0) return PCR_OK;
+    k_pack_xyz<float><<<div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, out);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+extern "C" {
+int pcr_pack_xyz_f32(pcr_ctx *ctx, const float *xyz, int n, float *xyzw) {
+    if (!ctx || n < 0) return PCR_ERR_INVALID;
+    if (n == 0) return PCR_OK;
+    k_pack_xyz<float><<<div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, (float4 *)xyzw);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+int pcr_pack_xyz_f64(pcr_ctx *ctx, const double *xyz, int n, float *xyzw) {
+    if (!ctx || n < 0) return PCR_ERR_INVALID;
+    if (n == 0) return PCR_OK;
+    k_pack_xyz<double><<<div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, (float4 *)xyzw);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+int pcr_unpack_xyz_f32(pcr_ctx *ctx, const float *xyzw, int n, float *xyz) {
+    if (!ctx || n < 0) return PCR_ERR_INVALID;
+    if (n == 0) return PCR_OK;
+    k_unpack_xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>((const float4 *)xyzw, n, xyz);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+}

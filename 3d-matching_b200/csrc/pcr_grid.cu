@@ -1,0 +1,272 @@
+// pcr_grid.cu — device uniform-grid build (K2): bounds reduction, cell counting, exclusive scan, scatter.
+// Replaces the KD-tree builds inside every Open3D call of the reference (KDTreeFlann).
+//
+// HBM roofline: algorithmic bytes = 16 n (read) + 4 n (cell ids) + 16 n (sorted write) + 4 (ncells+1).
+#include "pcr_common.cuh"
+
+// order-preserving float <-> int mapping for atomicMin/Max
+__device__ __forceinline__ int f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+static inline float ord2f_host(int i) {
+    const int j = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &j, 4);
+    return f;
+}
+
+__global__ void k_bounds_init(int *b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;       // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000;  // max
+}
+
+__global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, int n, int *__restrict__ b) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(pts + i);
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            atomicMin(b + d, f2ord(lo[d]));
+            atomicMax(b + 3 + d, f2ord(hi[d]));
+        }
+    }
+}
+
+int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]) {
+    PCR_ALLOC(b, int, 8);
+    k_bounds_init<<<1, 32, 0, ctx->stream>>>(b);
+    PCR_LAUNCHED();
+    const int blocks = min(div_up(n, 256), ctx->sm_count * 8);
+    k_bounds<<<blocks, 256, 0, ctx->stream>>>(pts, n, b);
+    PCR_LAUNCHED();
+    int *hb = (int *)ctx->pinned;
+    PCR_CUDA(cudaMemcpyAsync(hb, b, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < 3; d++) {
+        lo[d] = ord2f_host(hb[d]);
+        hi[d] = ord2f_host(hb[3 + d]);
+    }
+    return PCR_OK;
+}
+
+// ---- exclusive scan (3 phases: tile sums, scan of tile sums, tile scan + offset) -------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const T *__restrict__ data, long long n, T *__restrict__ sums) {
+    constexpr int ITEMS = 4;
+    const long long base = (long long)blockIdx.x * (1024 * ITEMS);
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const long long i = base + (long long)k * 1024 + threadIdx.x;
+        if (i < n) s += data[i];
+    }
+    __shared__ T ws[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = v;
+    }
+}
+
+// single block: exclusive scan of m tile sums in place; total -> sums[m]
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_sums(T *__restrict__ sums, int m) {
+    __shared__ T ws[32];
+    __shared__ T carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const T v = i < m ? sums[i] : (T)0;
+        T x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            T w = ws[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const T y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            ws[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const T warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : (T)0;
+        const T incl = x + warp_off + carry;
+        if (i < m) sums[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[m] = carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_tiles(T *__restrict__ data, long long n, const T *__restrict__ sums) {
+    constexpr int ITEMS = 4;
+    // thread t owns ITEMS consecutive elements so the tile is scanned in memory order
+    const long long base = (long long)blockIdx.x * (1024 * ITEMS) + (long long)threadIdx.x * ITEMS;
+    T v[ITEMS];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        v[k] = (base + k < n) ? data[base + k] : (T)0;
+        s += v[k];
+    }
+    __shared__ T ws[32];
+    T x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T w = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T y = __shfl_up_sync(0xffffffffu, w, o);
+            if (threadIdx.x >= o) w += y;
+        }
+        ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    T run = (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : (T)0) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        if (base + k < n) data[base + k] = run;
+        run += v[k];
+    }
+}
+
+template <typename T>
+static int exclusive_scan_impl(pcr_ctx *ctx, T *data, long long n) {
+    // data has n+1 slots; data[n] receives the total
+    const int tiles = div_up(n, 4096);
+    PCR_ALLOC(sums, T, (size_t)tiles + 1);
+    k_scan_tile_sums<T><<<tiles, 1024, 0, ctx->stream>>>(data, n, sums);
+    PCR_LAUNCHED();
+    k_scan_sums<T><<<1, 1024, 0, ctx->stream>>>(sums, tiles);
+    PCR_LAUNCHED();
+    k_scan_tiles<T><<<tiles, 1024, 0, ctx->stream>>>(data, n, sums);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaMemcpyAsync(data + n, sums + tiles, sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_exclusive_scan_u32(pcr_ctx *ctx, uint32_t *data, long long n) { return exclusive_scan_impl<uint32_t>(ctx, data, n); }
+int pcr_exclusive_scan_u64(pcr_ctx *ctx, unsigned long long *data, long long n) {
+    return exclusive_scan_impl<unsigned long long>(ctx, data, n);
+}
+
+// ---- cell counting and scatter ---------------------------------------------------------------------------
+struct GridDims {
+    double ox, oy, oz, inv_h;
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ uint32_t cell_of(const GridDims &g, const float4 &p) {
+    int cx = (int)floor(((double)p.x - g.ox) * g.inv_h);
+    int cy = (int)floor(((double)p.y - g.oy) * g.inv_h);
+    int cz = (int)floor(((double)p.z - g.oz) * g.inv_h);
+    cx = min(max(cx, 0), g.nx - 1);
+    cy = min(max(cy, 0), g.ny - 1);
+    cz = min(max(cz, 0), g.nz - 1);
+    return (uint32_t)((cz * g.ny + cy) * g.nx + cx);
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(const float4 *__restrict__ pts, int n, GridDims g,
+                                                    uint32_t *__restrict__ cell, uint32_t *__restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell_of(g, __ldg(pts + i));
+    cell[i] = c;
+    atomicAdd(count + c, 1u);
+}
+
+// pos = start[c] + (number of points of cell c placed before): the slot order inside a cell follows the atomic
+// arrival order, which no result depends on (ties are broken by original index, sums are fixed point).
+__global__ void __launch_bounds__(256) k_cell_scatter(const float4 *__restrict__ pts, int n,
+                                                      const uint32_t *__restrict__ cell,
+                                                      const uint32_t *__restrict__ start, uint32_t *__restrict__ fill,
+                                                      float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell[i];
+    const uint32_t pos = start[c] + atomicAdd(fill + c, 1u);
+    float4 p = __ldg(pts + i);
+    p.w = __int_as_float(i);
+    sorted[pos] = p;
+}
+
+int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo_in, const float *hi_in,
+                   Grid *g) {
+    if (n <= 0 || !(radius > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: n=%d radius=%g", n, radius);
+    float lo[3], hi[3];
+    if (lo_in && hi_in) {
+        for (int d = 0; d < 3; d++) { lo[d] = lo_in[d]; hi[d] = hi_in[d]; }
+    } else {
+        PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));
+    }
+    for (int d = 0; d < 3; d++)
+        if (!(lo[d] <= hi[d]) || isinf(lo[d]) || isinf(hi[d]))
+            return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: non-finite coordinates");
+    // cell size: radius with a 2^-10 margin, enlarged (x1.25 steps) until the dense table fits the budget
+    double h = radius * (1.0 + 1.0 / 1024.0);
+    long long nx, ny, nz;
+    for (;;) {
+        nx = (long long)floor(((double)hi[0] - (double)lo[0]) / h) + 1;
+        ny = (long long)floor(((double)hi[1] - (double)lo[1]) / h) + 1;
+        nz = (long long)floor(((double)hi[2] - (double)lo[2]) / h) + 1;
+        if ((double)nx * (double)ny * (double)nz <= (double)PCR_MAX_GRID_CELLS) break;
+        h *= 1.25;
+    }
+    const long long ncells = nx * ny * nz;
+    GridDims gd{(double)lo[0], (double)lo[1], (double)lo[2], 1.0 / h, (int)nx, (int)ny, (int)nz};
+    PCR_ALLOC(cell, uint32_t, (size_t)n);
+    PCR_ALLOC(start, uint32_t, (size_t)ncells + 1);
+    PCR_ALLOC(fill, uint32_t, (size_t)ncells);
+    PCR_ALLOC(sorted, float4, (size_t)n);
+    PCR_CUDA(cudaMemsetAsync(start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), ctx->stream));
+    PCR_CUDA(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)ncells, ctx->stream));
+    k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, start);
+    PCR_LAUNCHED();
+    PCR_TRY(pcr_exclusive_scan_u32(ctx, start, ncells));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, start, fill, sorted);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    g->sorted = sorted;
+    g->start = start;
+    g->ox = gd.ox; g->oy = gd.oy; g->oz = gd.oz;
+    g->inv_h = gd.inv_h;
+    g->h = h;
+    g->nx = gd.nx; g->ny = gd.ny; g->nz = gd.nz;
+    g->n = n;
+    return PCR_OK;
+}

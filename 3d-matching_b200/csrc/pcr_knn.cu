@@ -1,0 +1,454 @@
+// pcr_knn.cu — hybrid kNN (K3/K4 search), normal estimation (K3) and SPFH/FPFH (K4, K5).
+//
+// Replaces, on the reference's path:
+//   KDTreeFlann::SearchHybrid                           -> k_knn
+//   pcd.estimate_normals(Hybrid(2v,30))  src/ply/ply.py:110-112,133-135 (A.2) -> k_knn<MODE_NORMAL> + k_normals_solve
+//   compute_fpfh_feature(Hybrid(5v,100)) src/ply/ply.py:117-120         (A.4) -> k_knn<MODE_LIST> + k_spfh + k_fpfh
+//
+// Search design: one warp per query.  The 3x3x3 cell probe is 9 contiguous row ranges of the cell-sorted
+// cloud (x-fastest cell order), so lanes read consecutive float4s (coalesced).  In-radius candidates are
+// appended to a per-warp shared-memory buffer as 64-bit keys (fp32 d2 bits << 32 | index): key order IS the
+// (d2, index) order of determinism rule D2.  A warp-wide bitonic sort of the buffer yields the neighbour
+// list; when the buffer fills it is sorted and truncated to max_nn and the admission threshold tightens.
+#include "pcr_common.cuh"
+
+constexpr int KNN_WARPS = 4;
+constexpr int KNN_CAP = 1024;  // keys per warp (8 KB)
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void warp_bitonic_sort(u64 *buf, int n_pow2, int lane) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (n_pow2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const u64 a = buf[i], b = buf[l];
+                const bool up = ((i & k) == 0);
+                if ((a > b) == up) {
+                    buf[i] = b;
+                    buf[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// sort buf[0..cnt) ascending; returns nothing.  Pads to a power of two with ~0.
+__device__ __forceinline__ void warp_sort_prefix(u64 *buf, int cnt, int lane) {
+    const int p = next_pow2(cnt < 2 ? 2 : cnt);
+    for (int t = cnt + lane; t < p; t += 32) buf[t] = ~0ull;
+    __syncwarp();
+    warp_bitonic_sort(buf, p, lane);
+}
+
+// Collect the hybrid neighbour list of query (qx,qy,qz) into buf (sorted ascending); returns its length (<= max_nn).
+__device__ __forceinline__ int warp_knn_hybrid(const Grid &g, float qx, float qy, float qz, float r2, int max_nn,
+                                               u64 *buf, int lane) {
+    const int cx = grid_cell((double)qx, g.ox, g.inv_h, g.nx);
+    const int cy = grid_cell((double)qy, g.oy, g.inv_h, g.ny);
+    const int cz = grid_cell((double)qz, g.oz, g.inv_h, g.nz);
+    u64 thr = ((u64)__float_as_uint(r2)) << 32;  // d2 < r2  <=>  key < thr  (d2 >= 0)
+    int cnt = 0;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    if (x0 <= x1) {
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+        for (int z = z0; z <= z1; z++) {
+            for (int y = y0; y <= y1; y++) {
+                const long long row = ((long long)z * g.ny + y) * g.nx;
+                const uint32_t b = __ldg(g.start + row + x0);
+                const uint32_t e = __ldg(g.start + row + x1 + 1);
+                for (uint32_t base = b; base < e; base += 32) {
+                    const uint32_t k = base + lane;
+                    bool pred = false;
+                    u64 key = 0;
+                    if (k < e) {
+                        const float4 p = __ldg(g.sorted + k);
+                        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                        key = (((u64)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                        pred = key < thr;
+                    }
+                    if (cnt + 32 > KNN_CAP) {  // warp-uniform: make room
+                        __syncwarp();
+                        warp_sort_prefix(buf, cnt, lane);
+                        if (cnt > max_nn) cnt = max_nn;
+                        if (cnt == max_nn) thr = buf[max_nn - 1];
+                        __syncwarp();
+                        pred = pred && key < thr;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, pred);
+                    if (pred) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+                    cnt += __popc(m);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (cnt > 1) warp_sort_prefix(buf, cnt, lane);
+    __syncwarp();
+    return cnt < max_nn ? cnt : max_nn;
+}
+
+// ---- MODE_LIST: neighbour lists to global memory ------------------------------------------------------------
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_list(const float4 *__restrict__ queries, int nq, Grid g,
+                                                             float r2, int max_nn, int *__restrict__ idx,
+                                                             float *__restrict__ d2, int *__restrict__ cnt_out) {
+    __shared__ u64 sbuf[KNN_WARPS][KNN_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *buf = sbuf[warp];
+    for (int q = blockIdx.x * KNN_WARPS + warp; q < nq; q += gridDim.x * KNN_WARPS) {
+        const float4 p = __ldg(queries + q);
+        const int c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
+        for (int k = lane; k < max_nn; k += 32) {
+            const bool v = k < c;
+            const u64 key = v ? buf[k] : 0ull;
+            idx[(size_t)q * max_nn + k] = v ? (int)(uint32_t)(key & 0xffffffffull) : -1;
+            d2[(size_t)q * max_nn + k] = v ? __uint_as_float((uint32_t)(key >> 32)) : 0.0f;
+        }
+        if (lane == 0) cnt_out[q] = c;
+        __syncwarp();
+    }
+}
+
+// ---- MODE_NORMAL: covariance of the neighbourhood (A.2 cumulants, sequential in neighbour order) -----------------
+// cov_out: 6 doubles per query (c00 c01 c02 c11 c12 c22); the eigen-solve runs one query per thread afterwards.
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__restrict__ pts, int n, Grid g, float r2,
+                                                            int max_nn, double *__restrict__ cov_out) {
+    __shared__ u64 sbuf[KNN_WARPS][KNN_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *buf = sbuf[warp];
+    for (int q = blockIdx.x * KNN_WARPS + warp; q < n; q += gridDim.x * KNN_WARPS) {
+        const float4 p = __ldg(pts + q);
+        const int c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
+        double cu = 0.0;
+        if (c >= 3 && lane < 9) {
+            for (int k = 0; k < c; k++) {
+                const int j = (int)(uint32_t)(buf[k] & 0xffffffffull);
+                const float4 pj = __ldg(pts + j);
+                const double x = pj.x, y = pj.y, z = pj.z;
+                double term;
+                switch (lane) {
+                    case 0: term = x; break;
+                    case 1: term = y; break;
+                    case 2: term = z; break;
+                    case 3: term = x * x; break;
+                    case 4: term = x * y; break;
+                    case 5: term = x * z; break;
+                    case 6: term = y * y; break;
+                    case 7: term = y * z; break;
+                    default: term = z * z; break;
+                }
+                cu = cu + term;
+            }
+            cu = cu / (double)c;
+        }
+        double m[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) m[i] = __shfl_sync(0xffffffffu, cu, i);
+        if (lane == 0) {
+            double *o = cov_out + (size_t)q * 6;
+            if (c < 3) {
+                o[0] = 1.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1.0; o[4] = 0.0; o[5] = 1.0;
+            } else {
+                o[0] = m[3] - m[0] * m[0];
+                o[1] = m[4] - m[0] * m[1];
+                o[2] = m[5] - m[0] * m[2];
+                o[3] = m[6] - m[1] * m[1];
+                o[4] = m[7] - m[1] * m[2];
+                o[5] = m[8] - m[2] * m[2];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- robust symmetric 3x3 eigen-solver (A.2 FastEigen3x3 restated) ------------------------------------------------
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3_cross(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double d3_dot(D3 a, D3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ D3 d3_scale(D3 a, double s) { return D3{a.x * s, a.y * s, a.z * s}; }
+
+__device__ D3 eigvec0(const double *A, double ev) {
+    const D3 r0{A[0] - ev, A[1], A[2]};
+    const D3 r1{A[1], A[3] - ev, A[4]};
+    const D3 r2{A[2], A[4], A[5] - ev};
+    const D3 c01 = d3_cross(r0, r1), c02 = d3_cross(r0, r2), c12 = d3_cross(r1, r2);
+    const double d0 = d3_dot(c01, c01), d1 = d3_dot(c02, c02), d2 = d3_dot(c12, c12);
+    double dmax = d0;
+    int imax = 0;
+    if (d1 > dmax) { dmax = d1; imax = 1; }
+    if (d2 > dmax) { imax = 2; }
+    if (imax == 0) return d3_scale(c01, 1.0 / sqrt(d0));
+    if (imax == 1) return d3_scale(c02, 1.0 / sqrt(d1));
+    return d3_scale(c12, 1.0 / sqrt(d2));
+}
+
+__device__ D3 eigvec1(const double *A, D3 e0, double ev1) {
+    D3 U, V;
+    if (fabs(e0.x) > fabs(e0.y)) {
+        const double inv = 1.0 / sqrt(e0.x * e0.x + e0.z * e0.z);
+        U = D3{-e0.z * inv, 0.0, e0.x * inv};
+    } else {
+        const double inv = 1.0 / sqrt(e0.y * e0.y + e0.z * e0.z);
+        U = D3{0.0, e0.z * inv, -e0.y * inv};
+    }
+    V = d3_cross(e0, U);
+    const D3 AU{(A[0] * U.x + A[1] * U.y) + A[2] * U.z, (A[1] * U.x + A[3] * U.y) + A[4] * U.z,
+                (A[2] * U.x + A[4] * U.y) + A[5] * U.z};
+    const D3 AV{(A[0] * V.x + A[1] * V.y) + A[2] * V.z, (A[1] * V.x + A[3] * V.y) + A[4] * V.z,
+                (A[2] * V.x + A[4] * V.y) + A[5] * V.z};
+    double m00 = d3_dot(U, AU) - ev1;
+    double m01 = d3_dot(U, AV);
+    double m11 = d3_dot(V, AV) - ev1;
+    const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+    if (a00 >= a11) {
+        const double mx = a00 > a01 ? a00 : a01;
+        if (mx > 0) {
+            if (a00 >= a01) { m01 /= m00; m00 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m00; }
+            else { m00 /= m01; m01 = 1.0 / sqrt(1.0 + m00 * m00); m00 *= m01; }
+            return D3{m01 * U.x - m00 * V.x, m01 * U.y - m00 * V.y, m01 * U.z - m00 * V.z};
+        }
+        return U;
+    } else {
+        const double mx = a11 > a01 ? a11 : a01;
+        if (mx > 0) {
+            if (a11 >= a01) { m01 /= m11; m11 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m11; }
+            else { m11 /= m01; m01 = 1.0 / sqrt(1.0 + m11 * m11); m11 *= m01; }
+            return D3{m11 * U.x - m01 * V.x, m11 * U.y - m01 * V.y, m11 * U.z - m01 * V.z};
+        }
+        return U;
+    }
+}
+
+__device__ D3 fast_eigen3x3(const double *C) {
+    double A[6];
+    double mc = C[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) if (C[i] > mc) mc = C[i];
+    if (mc == 0.0) return D3{0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 6; i++) A[i] = C[i] / mc;
+    const double norm = (A[1] * A[1] + A[2] * A[2]) + A[4] * A[4];
+    if (norm > 0.0) {
+        const double q = ((A[0] + A[3]) + A[5]) / 3.0;
+        const double b00 = A[0] - q, b11 = A[3] - q, b22 = A[5] - q;
+        const double p = sqrt((((b00 * b00 + b11 * b11) + b22 * b22) + norm * 2.0) / 6.0);
+        const double c00 = b11 * b22 - A[4] * A[4];
+        const double c01 = A[1] * b22 - A[4] * A[2];
+        const double c02 = A[1] * A[4] - b11 * A[2];
+        const double det = ((b00 * c00 - A[1] * c01) + A[2] * c02) / ((p * p) * p);
+        double half_det = det * 0.5;
+        if (half_det < -1.0) half_det = -1.0;
+        if (half_det > 1.0) half_det = 1.0;
+        const double angle = pcr_acos(half_det) / 3.0;
+        const double two_thirds_pi = 2.09439510239319549;
+        const double beta2 = pcr_cos(angle) * 2.0;
+        const double beta0 = pcr_cos(angle + two_thirds_pi) * 2.0;
+        const double beta1 = -(beta0 + beta2);
+        const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+        if (half_det >= 0.0) {
+            const D3 v2 = eigvec0(A, e2);
+            if (e2 < e0 && e2 < e1) return v2;
+            const D3 v1 = eigvec1(A, v2, e1);
+            if (e1 < e0 && e1 < e2) return v1;
+            return d3_cross(v1, v2);
+        } else {
+            const D3 v0 = eigvec0(A, e0);
+            if (e0 < e1 && e0 < e2) return v0;
+            const D3 v1 = eigvec1(A, v0, e1);
+            if (e1 < e0 && e1 < e2) return v1;
+            return d3_cross(v0, v1);
+        }
+    }
+    D3 r{0, 0, 1};
+    if (C[0] < C[3] && C[0] < C[5]) { r.x = 1; r.z = 0; }
+    else if (C[3] < C[0] && C[3] < C[5]) { r.y = 1; r.z = 0; }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_normals_solve(const double *__restrict__ cov, int n, float4 *__restrict__ normals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double C[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) C[k] = cov[(size_t)i * 6 + k];
+    D3 nr = fast_eigen3x3(C);
+    const double len = sqrt(d3_dot(nr, nr));
+    if (len == 0.0 || isnan(len)) nr = D3{0, 0, 1};
+    normals[i] = make_float4((float)nr.x, (float)nr.y, (float)nr.z, 0.0f);
+}
+
+// ---- FPFH (A.4) -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_features(float4 p1f, float4 n1f, float4 p2f, float4 n2f, double *f) {
+    D3 n1{n1f.x, n1f.y, n1f.z}, n2{n2f.x, n2f.y, n2f.z};
+    D3 d{(double)p2f.x - (double)p1f.x, (double)p2f.y - (double)p1f.y, (double)p2f.z - (double)p1f.z};
+    f[0] = f[1] = f[2] = f[3] = 0.0;
+    const double len = sqrt(d3_dot(d, d));
+    if (len == 0.0) return;
+    f[3] = len;
+    const double a1 = d3_dot(n1, d) / len;
+    const double a2 = d3_dot(n2, d) / len;
+    if (pcr_acos(fabs(a1)) > pcr_acos(fabs(a2))) {
+        const D3 t = n1; n1 = n2; n2 = t;
+        d.x = -d.x; d.y = -d.y; d.z = -d.z;
+        f[2] = -a2;
+    } else {
+        f[2] = a1;
+    }
+    D3 v = d3_cross(d, n1);
+    const double vn = sqrt(d3_dot(v, v));
+    if (vn == 0.0) { f[0] = f[1] = f[2] = f[3] = 0.0; return; }
+    v.x /= vn; v.y /= vn; v.z /= vn;
+    const D3 w = d3_cross(n1, v);
+    f[1] = d3_dot(v, n2);
+    f[0] = pcr_atan2(d3_dot(w, n2), d3_dot(n1, n2));
+}
+
+__device__ __forceinline__ int clamp_bin(double x) {
+    int h = (int)floor(x);
+    if (h < 0) h = 0;
+    if (h >= 11) h = 10;
+    return h;
+}
+
+// one warp per point: lanes over neighbours 1..c-1 (position 0, the query itself, is skipped)
+__global__ void __launch_bounds__(128) k_spfh(const float4 *__restrict__ pts, const float4 *__restrict__ nrm, int n,
+                                              const int *__restrict__ idx, const int *__restrict__ cnt, int max_nn,
+                                              double *__restrict__ spfh) {
+    __shared__ int hist[4][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x * 4 + warp; i < n; i += gridDim.x * 4) {
+        hist[warp][lane] = 0;
+        if (lane == 0) hist[warp][32] = 0;
+        __syncwarp();
+        const int c = cnt[i];
+        const float4 p1 = __ldg(pts + i), n1 = __ldg(nrm + i);
+        for (int k = 1 + lane; k < c; k += 32) {
+            const int j = idx[(size_t)i * max_nn + k];
+            double f[4];
+            pair_features(p1, n1, __ldg(pts + j), __ldg(nrm + j), f);
+            atomicAdd(&hist[warp][clamp_bin(11.0 * (f[0] + PCR_PI) / (2.0 * PCR_PI))], 1);
+            atomicAdd(&hist[warp][11 + clamp_bin(11.0 * (f[1] + 1.0) * 0.5)], 1);
+            atomicAdd(&hist[warp][22 + clamp_bin(11.0 * (f[2] + 1.0) * 0.5)], 1);
+        }
+        __syncwarp();
+        const double inc = c > 1 ? 100.0 / (double)(c - 1) : 0.0;
+        for (int j = lane; j < 33; j += 32) {
+            const int h = hist[warp][j];
+            double v = 0.0;
+            for (int t = 0; t < h; t++) v = v + inc;  // the reference adds hist_incr once per neighbour
+            spfh[(size_t)i * 33 + j] = v;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx, const float *__restrict__ d2,
+                                              const int *__restrict__ cnt, int max_nn,
+                                              const double *__restrict__ spfh, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x * 4 + warp; i < n; i += gridDim.x * 4) {
+        const int c = cnt[i];
+        double F0 = 0.0, F1 = 0.0;  // bins lane and (lane 0 only) 32
+        double sum = 0.0;           // lanes 0..2: normaliser of block `lane`
+        if (c > 1) {
+            for (int k = 1; k < c; k++) {
+                const double dist = (double)d2[(size_t)i * max_nn + k];
+                if (dist == 0.0) continue;
+                const double *hs = spfh + (size_t)idx[(size_t)i * max_nn + k] * 33;
+                F0 = F0 + hs[lane] / dist;
+                if (lane == 0) F1 = F1 + hs[32] / dist;
+            }
+            if (lane < 3) {
+                for (int k = 1; k < c; k++) {
+                    const double dist = (double)d2[(size_t)i * max_nn + k];
+                    if (dist == 0.0) continue;
+                    const double *hs = spfh + (size_t)idx[(size_t)i * max_nn + k] * 33 + 11 * lane;
+#pragma unroll
+                    for (int j = 0; j < 11; j++) sum = sum + hs[j] / dist;
+                }
+                if (sum != 0.0) sum = 100.0 / sum;
+            }
+        }
+        const double s0 = __shfl_sync(0xffffffffu, sum, 0);
+        const double s1 = __shfl_sync(0xffffffffu, sum, 1);
+        const double s2 = __shfl_sync(0xffffffffu, sum, 2);
+        const double *hi = spfh + (size_t)i * 33;
+        if (c > 1) {
+            const double sj = lane < 11 ? s0 : (lane < 22 ? s1 : s2);
+            out[(size_t)i * 33 + lane] = (float)(F0 * sj + hi[lane]);
+            if (lane == 0) out[(size_t)i * 33 + 32] = (float)(F1 * s2 + hi[32]);
+        } else {
+            out[(size_t)i * 33 + lane] = 0.0f;
+            if (lane == 0) out[(size_t)i * 33 + 32] = 0.0f;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static int knn_blocks(pcr_ctx *ctx, int nq) { return min(div_up(nq, KNN_WARPS), ctx->sm_count * 16); }
+
+int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq, double radius, int max_nn, int *idx,
+                 float *d2, int *cnt) {
+    if (!(radius > 0.0) || max_nn < 1 || max_nn > KNN_CAP / 2)
+        return pcr_fail(ctx, PCR_ERR_INVALID, "knn: radius must be > 0 and 1 <= max_nn <= %d", KNN_CAP / 2);
+    if (nq == 0) return PCR_OK;
+    if (n == 0) {
+        PCR_CUDA(cudaMemsetAsync(idx, 0xff, sizeof(int) * (size_t)nq * max_nn, ctx->stream));
+        PCR_CUDA(cudaMemsetAsync(d2, 0, sizeof(float) * (size_t)nq * max_nn, ctx->stream));
+        PCR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)nq, ctx->stream));
+        return PCR_OK;
+    }
+    Grid g;
+    PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
+    k_knn_list<<<knn_blocks(ctx, nq), KNN_WARPS * 32, 0, ctx->stream>>>(q, nq, g, (float)(radius * radius), max_nn, idx,
+                                                                        d2, cnt);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int max_nn, float4 *normals) {
+    if (!(radius > 0.0) || max_nn < 1 || max_nn > KNN_CAP / 2)
+        return pcr_fail(ctx, PCR_ERR_INVALID, "normals: radius must be > 0 and 1 <= max_nn <= %d", KNN_CAP / 2);
+    if (n == 0) return PCR_OK;
+    Grid g;
+    PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
+    PCR_ALLOC(cov, double, (size_t)n * 6);
+    // queries are visited in cell-sorted order for locality: use the sorted copy as the query list
+    k_knn_cov<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+    PCR_LAUNCHED();
+    k_normals_solve<<<div_up(n, 128), 128, 0, ctx->stream>>>(cov, n, normals);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_fpfh_impl(pcr_ctx *ctx, const float4 *pts, const float4 *nrm, int n, double radius, int max_nn, float *out) {
+    if (!(radius > 0.0) || max_nn < 1 || max_nn > KNN_CAP / 2)
+        return pcr_fail(ctx, PCR_ERR_INVALID, "fpfh: radius must be > 0 and 1 <= max_nn <= %d", KNN_CAP / 2);
+    if (n == 0) return PCR_OK;
+    Grid g;
+    PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
+    PCR_ALLOC(idx, int, (size_t)n * max_nn);
+    PCR_ALLOC(d2, float, (size_t)n * max_nn);
+    PCR_ALLOC(cnt, int, (size_t)n);
+    PCR_ALLOC(spfh, double, (size_t)n * 33);
+    k_knn_list<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, idx,
+                                                                       d2, cnt);
+    PCR_LAUNCHED();
+    const int blocks = min(div_up(n, 4), ctx->sm_count * 16);
+    k_spfh<<<blocks, 128, 0, ctx->stream>>>(pts, nrm, n, idx, cnt, max_nn, spfh);
+    PCR_LAUNCHED();
+    k_fpfh<<<blocks, 128, 0, ctx->stream>>>(n, idx, d2, cnt, max_nn, spfh, out);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}

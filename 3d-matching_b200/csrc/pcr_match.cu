@@ -1,0 +1,110 @@
+// pcr_match.cu — FPFH feature matching (K6), replaces open3d CorrespondencesFromFeatures as reached from
+// src/matcher/ransac.py:85 and from registration_ransac_based_on_feature_matching (src/matcher/ransac.py:42-47)
+// (1-NN in 33-D per source descriptor, optional mutual filter with the 10 % fall-back).
+//
+// Distance specification: fp64 sequential accumulation over the fp32 descriptors, ties -> lowest index.
+// k_nn_features_exact evaluates it for every pair (CUDA-core fp64, smem-staged tiles, broadcast reads).
+#include "pcr_common.cuh"
+
+constexpr int NNF_THREADS = 128;
+constexpr int NNF_TILE = 64;
+
+__global__ void __launch_bounds__(NNF_THREADS) k_nn_features_exact(const float *__restrict__ fq, int nq,
+                                                                   const float *__restrict__ fb, int nb,
+                                                                   int *__restrict__ nn) {
+    __shared__ float tile[NNF_TILE][33];
+    const int q = blockIdx.x * NNF_THREADS + threadIdx.x;
+    float a[33];
+#pragma unroll
+    for (int k = 0; k < 33; k++) a[k] = (q < nq) ? fq[(size_t)q * 33 + k] : 0.0f;
+    double best = INFINITY;
+    int bi = -1;
+    for (int base = 0; base < nb; base += NNF_TILE) {
+        const int tn = min(NNF_TILE, nb - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < tn * 33; t += NNF_THREADS) tile[t / 33][t % 33] = fb[(size_t)base * 33 + t];
+        __syncthreads();
+        for (int j = 0; j < tn; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 33; k++) {
+                const double df = (double)a[k] - (double)tile[j][k];
+                acc = acc + df * df;
+            }
+            if (acc < best) {
+                best = acc;
+                bi = base + j;
+            }
+        }
+    }
+    if (q < nq) nn[q] = bi;
+}
+
+__global__ void __launch_bounds__(256) k_mutual_flags(const int *__restrict__ nn_s, const int *__restrict__ nn_t, int ms,
+                                                      uint32_t *__restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ms) return;
+    const int j = nn_s[i];
+    flags[i] = (j >= 0 && nn_t[j] == i) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_corr_compact(const int *__restrict__ nn_s, const uint32_t *__restrict__ pos,
+                                                      int ms, int *__restrict__ corr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ms) return;
+    if (pos[i + 1] != pos[i]) {
+        corr[2 * (size_t)pos[i]] = i;
+        corr[2 * (size_t)pos[i] + 1] = nn_s[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_corr_all(const int *__restrict__ nn_s, int ms, int *__restrict__ corr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ms) return;
+    corr[2 * (size_t)i] = i;
+    corr[2 * (size_t)i + 1] = nn_s[i];
+}
+
+int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn) {
+    if (nq == 0) return PCR_OK;
+    if (nb == 0) {
+        PCR_CUDA(cudaMemsetAsync(nn, 0xff, sizeof(int) * (size_t)nq, ctx->stream));
+        return PCR_OK;
+    }
+    k_nn_features_exact<<<div_up(nq, NNF_THREADS), NNF_THREADS, 0, ctx->stream>>>(fq, nq, fb, nb, nn);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int mt, int mutual, double mutual_ratio,
+                   int *corr, int *c_host) {
+    *c_host = 0;
+    if (ms == 0 || mt == 0) return PCR_OK;
+    PCR_ALLOC(nn_s, int, (size_t)ms);
+    PCR_TRY(pcr_nn_features_impl(ctx, fs, ms, ft, mt, nn_s));
+    if (mutual) {
+        PCR_ALLOC(nn_t, int, (size_t)mt);
+        PCR_ALLOC(pos, uint32_t, (size_t)ms + 1);
+        PCR_TRY(pcr_nn_features_impl(ctx, ft, mt, fs, ms, nn_t));
+        k_mutual_flags<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, nn_t, ms, pos);
+        PCR_LAUNCHED();
+        PCR_TRY(pcr_exclusive_scan_u32(ctx, pos, ms));
+        k_corr_compact<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, pos, ms, corr);
+        PCR_LAUNCHED();
+        uint32_t *h = (uint32_t *)ctx->pinned;
+        PCR_CUDA(cudaMemcpyAsync(h, pos + ms, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int c = (int)*h;
+        if ((double)c >= mutual_ratio * (double)ms) {
+            *c_host = c;
+            return PCR_OK;
+        }
+        // too few mutual pairs: fall back to the one-directional set (A.5)
+    }
+    k_corr_all<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, ms, corr);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    *c_host = ms;
+    return PCR_OK;
+}

@@ -1,0 +1,514 @@
+// pcr_ransac.cu — batched RANSAC (K7 + K8), replaces registration_ransac_based_on_feature_matching as called
+// from src/matcher/ransac.py:42-59, and the NumPy manual-step functions
+// compute_step_transformation / evaluate_inlier_ratio(_fast) (src/matcher/ransac.py:104-277).
+//
+// Determinism (D6): hypothesis h draws its three correspondences from Philox4x32-10(counter = h, key = seed),
+// so the hypothesis stream is independent of wave size and GPU count; the winner is the one the sequential
+// single-thread Open3D loop would return (prefix-maximum replay in pcr_ransac_scan, on the host).
+//
+//   k_ransac_generate : one thread per hypothesis — sample, edge-length checker, 3-point Umeyama (Jacobi
+//                       eigen-solve of Sigma^T Sigma in fp64), distance checker, survivors appended.
+//   k_ransac_validate : one block per survivor — transform all source points (fp64 -> fp32), radius-limited
+//                       1-NN in the target grid, inlier count + fixed-point sum d2 (D5), correspondence
+//                       inlier count; survivors better than the running best are emitted as records.
+#include <algorithm>
+
+#include "pcr_common.cuh"
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void philox4x32_10(u64 ctr_lo, u64 ctr_hi, u64 key, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v_cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double v_dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 v_scale(V3 a, double s) { return V3{a.x * s, a.y * s, a.z * s}; }
+
+// cyclic Jacobi, 8 sweeps, on the symmetric 3x3 K; V columns = eigenvectors (same operation order as the oracle)
+__device__ void jacobi3(double K[3][3], double V[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 8; sweep++) {
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const int p = (e == 2) ? 1 : 0, q = (e == 0) ? 1 : 2;
+            const double apq = K[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (K[q][q] - K[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0);
+            const double s = t * c;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double kp = K[k][p], kq = K[k][q];
+                K[k][p] = c * kp - s * kq;
+                K[k][q] = s * kp + c * kq;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double pk = K[p][k], qk = K[q][k];
+                K[p][k] = c * pk - s * qk;
+                K[q][k] = s * pk + c * qk;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - s * vq;
+                V[k][q] = s * vp + c * vq;
+            }
+        }
+    }
+}
+
+// three source / target points (rows) -> T (12 doubles, rows 0..2 of the 4x4).  Always finite.
+__device__ void rigid3(const double s[3][3], const double t[3][3], double *T) {
+    double ms[3], mt[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        ms[d] = ((s[0][d] + s[1][d]) + s[2][d]) / 3.0;
+        mt[d] = ((t[0][d] + t[1][d]) + t[2][d]) / 3.0;
+    }
+    double a[3][3], b[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            a[k][d] = s[k][d] - ms[d];
+            b[k][d] = t[k][d] - mt[d];
+        }
+    double S[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S[i][j] = ((b[0][i] * a[0][j] + b[1][i] * a[1][j]) + b[2][i] * a[2][j]) / 3.0;
+    double K[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K[i][j] = (S[0][i] * S[0][j] + S[1][i] * S[1][j]) + S[2][i] * S[2][j];
+    jacobi3(K, V);
+    int o0 = 0, o1 = 1, o2 = 2;
+    double l0 = K[0][0], l1 = K[1][1], l2 = K[2][2];
+    if (l1 > l0) { double tl = l0; l0 = l1; l1 = tl; int to = o0; o0 = o1; o1 = to; }
+    if (l2 > l1) { double tl = l1; l1 = l2; l2 = tl; int to = o1; o1 = o2; o2 = to; }
+    if (l1 > l0) { double tl = l0; l0 = l1; l1 = tl; int to = o0; o0 = o1; o1 = to; }
+    // select columns o0, o1 of V without dynamic register indexing
+    V3 v1, v2;
+    v1.x = o0 == 0 ? V[0][0] : (o0 == 1 ? V[0][1] : V[0][2]);
+    v1.y = o0 == 0 ? V[1][0] : (o0 == 1 ? V[1][1] : V[1][2]);
+    v1.z = o0 == 0 ? V[2][0] : (o0 == 1 ? V[2][1] : V[2][2]);
+    v2.x = o1 == 0 ? V[0][0] : (o1 == 1 ? V[0][1] : V[0][2]);
+    v2.y = o1 == 0 ? V[1][0] : (o1 == 1 ? V[1][1] : V[1][2]);
+    v2.z = o1 == 0 ? V[2][0] : (o1 == 1 ? V[2][1] : V[2][2]);
+    const V3 v3 = v_cross(v1, v2);
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    V3 w1{(S[0][0] * v1.x + S[0][1] * v1.y) + S[0][2] * v1.z, (S[1][0] * v1.x + S[1][1] * v1.y) + S[1][2] * v1.z,
+          (S[2][0] * v1.x + S[2][1] * v1.y) + S[2][2] * v1.z};
+    const double n1 = sqrt(v_dot(w1, w1));
+    if (n1 > 0.0 && !isnan(n1) && !isinf(n1)) {
+        const V3 u1 = v_scale(w1, 1.0 / n1);
+        V3 w2{(S[0][0] * v2.x + S[0][1] * v2.y) + S[0][2] * v2.z, (S[1][0] * v2.x + S[1][1] * v2.y) + S[1][2] * v2.z,
+              (S[2][0] * v2.x + S[2][1] * v2.y) + S[2][2] * v2.z};
+        double pr = v_dot(w2, u1);
+        w2.x -= pr * u1.x; w2.y -= pr * u1.y; w2.z -= pr * u1.z;
+        double n2 = sqrt(v_dot(w2, w2));
+        if (!(n2 > n1 * 1e-10)) {
+            w2 = v2;
+            pr = v_dot(w2, u1);
+            w2.x -= pr * u1.x; w2.y -= pr * u1.y; w2.z -= pr * u1.z;
+            n2 = sqrt(v_dot(w2, w2));
+            if (!(n2 > 1e-6)) {
+                w2 = v3;
+                pr = v_dot(w2, u1);
+                w2.x -= pr * u1.x; w2.y -= pr * u1.y; w2.z -= pr * u1.z;
+                n2 = sqrt(v_dot(w2, w2));
+            }
+        }
+        const V3 u2 = v_scale(w2, 1.0 / n2);
+        const V3 u3 = v_cross(u1, u2);
+        const double U[3][3] = {{u1.x, u2.x, u3.x}, {u1.y, u2.y, u3.y}, {u1.z, u2.z, u3.z}};
+        const double W[3][3] = {{v1.x, v2.x, v3.x}, {v1.y, v2.y, v3.y}, {v1.z, v2.z, v3.z}};
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) R[i][j] = (U[i][0] * W[j][0] + U[i][1] * W[j][1]) + U[i][2] * W[j][2];
+    }
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) T[4 * i + j] = R[i][j];
+        T[4 * i + 3] = mt[i] - ((R[i][0] * ms[0] + R[i][1] * ms[1]) + R[i][2] * ms[2]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) bad = bad || isnan(T[i]) || isinf(T[i]);
+    if (bad) {  // src/matcher/ransac.py:184-185
+#pragma unroll
+        for (int i = 0; i < 12; i++) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    }
+}
+
+struct Survivor {
+    long long hyp;
+    double T[12];
+};
+
+__device__ __forceinline__ void gather3(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
+                                        const int2 *__restrict__ corr, const int id[3], double s[3][3], double t[3][3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int2 c = __ldg(corr + id[k]);
+        const float4 p = __ldg(src + c.x), q = __ldg(tgt + c.y);
+        s[k][0] = p.x; s[k][1] = p.y; s[k][2] = p.z;
+        t[k][0] = q.x; t[k][1] = q.y; t[k][2] = q.z;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ransac_generate(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
+                                                         const int2 *__restrict__ corr, int c, double max_dist,
+                                                         double edge_sim, long long hyp_begin, long long count, u64 seed,
+                                                         Survivor *__restrict__ surv, unsigned int *__restrict__ n_surv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long h = hyp_begin + i;
+    uint32_t r[4];
+    philox4x32_10((u64)h, 0ull, seed, r);
+    int id[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) id[k] = (int)__umulhi(r[k], (uint32_t)c);  // (r * c) >> 32, with replacement
+    double s[3][3], t[3][3];
+    gather3(src, tgt, corr, id, s, t);
+    // CorrespondenceCheckerBasedOnEdgeLength
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = a + 1; b < 3; b++) {
+            const double ax = s[a][0] - s[b][0], ay = s[a][1] - s[b][1], az = s[a][2] - s[b][2];
+            const double bx = t[a][0] - t[b][0], by = t[a][1] - t[b][1], bz = t[a][2] - t[b][2];
+            const double ds = sqrt((ax * ax + ay * ay) + az * az), dt = sqrt((bx * bx + by * by) + bz * bz);
+            if (ds < dt * edge_sim || dt < ds * edge_sim) return;
+        }
+    double T[12];
+    rigid3(s, t, T);
+    // CorrespondenceCheckerBasedOnDistance
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double dx = (((T[0] * s[k][0] + T[1] * s[k][1]) + T[2] * s[k][2]) + T[3]) - t[k][0];
+        const double dy = (((T[4] * s[k][0] + T[5] * s[k][1]) + T[6] * s[k][2]) + T[7]) - t[k][1];
+        const double dz = (((T[8] * s[k][0] + T[9] * s[k][1]) + T[10] * s[k][2]) + T[11]) - t[k][2];
+        if (sqrt((dx * dx + dy * dy) + dz * dz) > max_dist) return;
+    }
+    const unsigned int slot = atomicAdd(n_surv, 1u);
+    surv[slot].hyp = h;
+#pragma unroll
+    for (int k = 0; k < 12; k++) surv[slot].T[k] = T[k];
+}
+
+constexpr int VAL_THREADS = 256;
+
+__global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
+    const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g, const int2 *__restrict__ corr, int c,
+    double max_dist, float r2, double sc_d, const Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
+    long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs, unsigned int *__restrict__ n_recs,
+    unsigned int rec_cap) {
+    __shared__ double sT[12];
+    __shared__ long long red[VAL_THREADS / 32][3];
+    const unsigned int ns = *n_surv;
+    for (unsigned int sidx = blockIdx.x; sidx < ns; sidx += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 12) sT[threadIdx.x] = surv[sidx].T[threadIdx.x];
+        __syncthreads();
+        double T[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) T[i] = sT[i];
+        long long cnt = 0, sumq = 0, cin = 0;
+        for (int i = threadIdx.x; i < ms; i += VAL_THREADS) {
+            const float4 p = __ldg(src + i);
+            const float3 q = xform_pt(T, p.x, p.y, p.z);
+            float d2;
+            const int j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+            if (j >= 0) {
+                cnt++;
+                sumq += fixed_ll((double)d2, sc_d);
+            }
+        }
+        for (int i = threadIdx.x; i < c; i += VAL_THREADS) {
+            const int2 cc = __ldg(corr + i);
+            const float4 p = __ldg(src_orig + cc.x), q = __ldg(tgt + cc.y);
+            const double x = p.x, y = p.y, z = p.z;
+            const double dx = (((T[0] * x + T[1] * y) + T[2] * z) + T[3]) - (double)q.x;
+            const double dy = (((T[4] * x + T[5] * y) + T[6] * z) + T[7]) - (double)q.y;
+            const double dz = (((T[8] * x + T[9] * y) + T[10] * z) + T[11]) - (double)q.z;
+            if (sqrt((dx * dx + dy * dy) + dz * dz) < max_dist) cin++;
+        }
+        cnt = warp_sum_ll(cnt);
+        sumq = warp_sum_ll(sumq);
+        cin = warp_sum_ll(cin);
+        if ((threadIdx.x & 31) == 0) {
+            red[threadIdx.x >> 5][0] = cnt;
+            red[threadIdx.x >> 5][1] = sumq;
+            red[threadIdx.x >> 5][2] = cin;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long a = 0, b = 0, d = 0;
+#pragma unroll
+            for (int w = 0; w < VAL_THREADS / 32; w++) { a += red[w][0]; b += red[w][1]; d += red[w][2]; }
+            // IsBetterRANSACThan against the running best at wave start (a necessary condition for being a
+            // prefix maximum of the sequential loop)
+            const bool better = a > best_cnt || (a == best_cnt && best_cnt > 0 && b < best_sumq);
+            if (better) {
+                const unsigned int slot = atomicAdd(n_recs, 1u);
+                if (slot < rec_cap) {
+                    pcr_hyp_record *o = recs + slot;
+                    o->hyp = surv[sidx].hyp;
+                    o->inlier_count = a;
+                    o->sum_d2_fixed = b;
+                    o->corr_inliers = (int)d;
+                    o->reserved = 0;
+#pragma unroll
+                    for (int i = 0; i < 12; i++) o->transformation[i] = sT[i];
+                }
+            }
+        }
+    }
+}
+
+// ---- manual-step twins -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ransac_step(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
+                                                     const int2 *__restrict__ corr, int c, u64 seed, long long h_begin,
+                                                     int count, double *__restrict__ T_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double *o = T_out + (size_t)i * 16;
+    if (c < 3) {  // src/matcher/ransac.py:138-140
+        for (int k = 0; k < 16; k++) o[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    uint32_t r[4];
+    philox4x32_10((u64)(h_begin + i), 1ull, seed, r);
+    int i0 = (int)__umulhi(r[0], (uint32_t)c);
+    int i1 = (int)__umulhi(r[1], (uint32_t)(c - 1));
+    int i2 = (int)__umulhi(r[2], (uint32_t)(c - 2));
+    if (i1 >= i0) i1++;
+    const int lo = min(i0, i1), hi = max(i0, i1);
+    if (i2 >= lo) i2++;
+    if (i2 >= hi) i2++;
+    const int id[3] = {i0, i1, i2};
+    double s[3][3], t[3][3], T[12];
+    gather3(src, tgt, corr, id, s, t);
+    rigid3(s, t, T);
+    for (int k = 0; k < 12; k++) o[k] = T[k];
+    o[12] = 0.0; o[13] = 0.0; o[14] = 0.0; o[15] = 1.0;
+}
+
+__global__ void __launch_bounds__(256) k_inlier_count(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
+                                                      const int2 *__restrict__ corr, int c, const double *__restrict__ Ts,
+                                                      double thresh, int squared, int *__restrict__ counts) {
+    __shared__ int red[8];
+    const double *T = Ts + (size_t)blockIdx.x * 16;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < c; i += 256) {
+        const int2 cc = __ldg(corr + i);
+        const float4 p = __ldg(src + cc.x), q = __ldg(tgt + cc.y);
+        const double x = p.x, y = p.y, z = p.z;
+        const double dx = (((T[0] * x + T[1] * y) + T[2] * z) + T[3]) - (double)q.x;
+        const double dy = (((T[4] * x + T[5] * y) + T[6] * z) + T[7]) - (double)q.y;
+        const double dz = (((T[8] * x + T[9] * y) + T[10] * z) + T[11]) - (double)q.z;
+        const double d2 = (dx * dx + dy * dy) + dz * dz;
+        if (squared ? (d2 < thresh) : (sqrt(d2) < thresh)) cnt++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; w++) s += red[w];
+        counts[blockIdx.x] = s;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+extern "C" int pcr_ransac_k_d(double max_dist, int ms) {
+    return 62 - 2 * pcr_pow2ceil_exp(max_dist) - pcr_ilog2ceil(ms > 1 ? ms : 1);
+}
+
+struct RansacWork {
+    Grid g;
+    const float4 *src_sorted;
+    float r2;
+    int k_d;
+};
+
+int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist,
+                       RansacWork *w) {
+    PCR_TRY(pcr_grid_build(ctx, tgt, mt, max_dist, nullptr, nullptr, &w->g));
+    // source in cell order of a grid over itself: lanes of a warp then probe neighbouring target cells
+    Grid gs;
+    PCR_TRY(pcr_grid_build(ctx, src, ms, max_dist * 2.0, nullptr, nullptr, &gs));
+    w->src_sorted = gs.sorted;
+    w->r2 = (float)(max_dist * max_dist);
+    w->k_d = pcr_ransac_k_d(max_dist, ms);
+    return PCR_OK;
+}
+
+// scores [hyp_begin, hyp_end): leaves up to cap records (unsorted) in the pinned buffer; counts returned
+int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt,
+                         const int *corr, int c, double max_dist, double edge_sim, long long hyp_begin,
+                         long long hyp_end, u64 seed, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
+                         int cap, int *n_recs_host, long long *n_surv_host) {
+    const long long count = hyp_end - hyp_begin;
+    *n_recs_host = 0;
+    *n_surv_host = 0;
+    if (count <= 0) return PCR_OK;
+    if (count > (1LL << 30)) return pcr_fail(ctx, PCR_ERR_INVALID, "wave too large");
+    const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
+    PCR_ALLOC(surv, Survivor, (size_t)count);
+    PCR_ALLOC(counters, unsigned int, 4);
+    PCR_ALLOC(recs, pcr_hyp_record, (size_t)cap);
+    PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
+    k_ransac_generate<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, max_dist, edge_sim,
+                                                                   hyp_begin, count, seed, surv, counters);
+    PCR_LAUNCHED();
+    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * 8);
+    k_ransac_validate<<<vblocks, VAL_THREADS, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
+                                                                w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt,
+                                                                best_sumq, recs, counters + 1, (unsigned int)cap);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    unsigned int *hc = (unsigned int *)ctx->pinned;
+    PCR_CUDA(cudaMemcpyAsync(hc, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_surv_host = hc[0];
+    const unsigned int nrec = hc[1];
+    ctx->cur_block = mark_block;
+    ctx->cur_off = mark_off;
+    if (nrec > (unsigned int)cap)
+        return pcr_fail(ctx, PCR_ERR_INVALID, "ransac wave produced %u records, capacity %d", nrec, cap);
+    if (nrec) {
+        PCR_CUDA(cudaMemcpyAsync(recs_host, recs, sizeof(pcr_hyp_record) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::sort(recs_host, recs_host + nrec, [](const pcr_hyp_record &a, const pcr_hyp_record &b) { return a.hyp < b.hyp; });
+    }
+    *n_recs_host = (int)nrec;
+    return PCR_OK;
+}
+
+extern "C" int pcr_ransac_scan(const pcr_hyp_record *recs, int n, int64_t hyp_begin, int64_t hyp_end, int c, int ms,
+                               double confidence, int32_t k_d, pcr_reg_result *st, int *stop) {
+    // Replays `for itr in [hyp_begin, hyp_end): if itr >= est_k: break; ...` of A.6 over the survivors that can
+    // change the state (records sorted by hyp).  st->est_k must be initialised to max_iter by the caller.
+    *stop = 0;
+    int64_t h_set = -1;
+    for (int i = 0; i < n; i++) {
+        const pcr_hyp_record &r = recs[i];
+        if (r.hyp < hyp_begin || r.hyp >= hyp_end) continue;
+        if (r.hyp >= st->est_k) break;
+        const bool better = r.inlier_count > st->inlier_count ||
+                            (r.inlier_count == st->inlier_count && st->inlier_count > 0 && r.sum_d2_fixed < st->sum_d2_fixed);
+        if (!better) continue;
+        st->inlier_count = r.inlier_count;
+        st->sum_d2_fixed = r.sum_d2_fixed;
+        st->best_hyp = r.hyp;
+        for (int k = 0; k < 12; k++) st->transformation[k] = r.transformation[k];
+        st->transformation[12] = st->transformation[13] = st->transformation[14] = 0.0;
+        st->transformation[15] = 1.0;
+        const double ratio = (double)r.corr_inliers / (double)c;
+        const double est = log(1.0 - confidence) / log(1.0 - ratio * ratio * ratio);
+        if (est >= 0.0 && est < (double)st->est_k) {
+            st->est_k = (int64_t)ceil(est);
+            h_set = r.hyp;
+        }
+    }
+    if (st->est_k <= hyp_end) {
+        *stop = 1;
+        int64_t ev = st->est_k;
+        if (h_set + 1 > ev) ev = h_set + 1;
+        if (hyp_begin > ev) ev = hyp_begin;
+        st->hyp_evaluated = ev;
+    } else {
+        st->hyp_evaluated = hyp_end;
+    }
+    st->k_d = k_d;
+    st->fitness = ms > 0 ? (double)st->inlier_count / (double)ms : 0.0;
+    st->inlier_rmse = st->inlier_count > 0 ? sqrt(ldexp((double)st->sum_d2_fixed, -k_d) / (double)st->inlier_count) : 0.0;
+    return PCR_OK;
+}
+
+static void reg_result_init(pcr_reg_result *r, int64_t max_iter) {
+    memset(r, 0, sizeof(*r));
+    r->transformation[0] = r->transformation[5] = r->transformation[10] = r->transformation[15] = 1.0;
+    r->best_hyp = -1;
+    r->est_k = max_iter;
+}
+
+int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, const int *corr, int c,
+                    double max_dist, double edge_sim, int64_t max_iter, double confidence, u64 seed,
+                    pcr_reg_result *res) {
+    reg_result_init(res, max_iter);
+    // Open3D returns the default result for ransac_n > |corr| or a non-positive threshold (A.6)
+    if (c < 3 || !(max_dist > 0.0) || ms == 0 || mt == 0 || max_iter <= 0) return PCR_OK;
+    RansacWork w;
+    PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
+    std::vector<pcr_hyp_record> recs;
+    int64_t begin = 0, wave = 4096;
+    int64_t survivors = 0;
+    while (begin < max_iter && begin < res->est_k) {
+        const int64_t end = std::min<int64_t>(max_iter, begin + wave);
+        int cap = 4096;
+        int nrec = 0;
+        long long nsurv = 0;
+        for (;;) {
+            recs.resize((size_t)cap);
+            const int rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, begin, end, seed,
+                                                res->inlier_count, res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
+            if (rc == PCR_OK) break;
+            if (rc == PCR_ERR_INVALID && cap < (1 << 24) && (int64_t)cap < end - begin) { cap *= 16; continue; }
+            return rc;
+        }
+        survivors += nsurv;
+        int stop = 0;
+        pcr_ransac_scan(recs.data(), nrec, begin, end, c, ms, confidence, w.k_d, res, &stop);
+        begin = end;
+        if (stop) break;
+        if (wave < (1 << 20)) wave *= 2;
+    }
+    res->survivors = survivors;
+    res->k_d = w.k_d;
+    if (res->hyp_evaluated > max_iter) res->hyp_evaluated = max_iter;
+    return PCR_OK;
+}
+
+int pcr_ransac_step_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, u64 seed,
+                         long long h_begin, int count, double *T) {
+    if (count <= 0) return PCR_OK;
+    k_ransac_step<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, seed, h_begin, count, T);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_inlier_count_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, const double *T,
+                          int count, double thresh, int squared, int *counts) {
+    if (count <= 0) return PCR_OK;
+    k_inlier_count<<<count, 256, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, T, thresh, squared, counts);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}

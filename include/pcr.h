@@ -1,0 +1,186 @@
+/*
+ * pcr.h — C ABI of the B200 point-cloud registration engine (libpcr_b200.so).
+ *
+ * Drop-in boundary for the reference's src/matcher hot path (KTC-Security-Circle/3d-matching).  The
+ * reference has no FFI of its own: its boundary is the Python surface of src/matcher/ + the Ply attribute
+ * protocol, and every heavy call goes to the open3d==0.19.0 wheel.  Each export below names the reference
+ * call site (file:line under /root/reference) it replaces.  The Python mirror that binds these symbols with
+ * ctypes is 3d-matching_b200/{matcher,ply,pcr_b200}; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns PCR_OK (0) or a negative pcr_status; it never throws; pcr_last_error(ctx)
+ *     returns the message of the last failure on that context.
+ *   - *_dev pointers are device pointers on the context's device; *_host pointers are host memory.
+ *   - clouds on the device are packed float4 (x, y, z, unused) — "xyzw"; normals likewise.
+ *   - FPFH descriptors are (n, 33) fp32 row-major (row = point; the reference's Feature.data is the (33, n)
+ *     transpose); correspondences are (c, 2) int32 [source index, target index]; transforms are 4x4
+ *     row-major fp64.
+ *   - work is enqueued on the stream given to pcr_set_stream (default: the legacy default stream); calls
+ *     that return host results synchronise that stream before returning.
+ *   - one context may be used by one thread at a time (PCR_ERR_BUSY otherwise); different contexts are
+ *     independent.  The library owns only per-context scratch; results go to caller-provided buffers.
+ */
+#ifndef PCR_H
+#define PCR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PCR_API __attribute__((visibility("default")))
+#else
+#define PCR_API
+#endif
+
+typedef enum pcr_status {
+    PCR_OK = 0,
+    PCR_ERR_INVALID = -1, /* bad argument (maps to ValueError) */
+    PCR_ERR_CUDA = -2,    /* CUDA runtime failure (RuntimeError) */
+    PCR_ERR_OOM = -3,     /* device allocation failed (MemoryError) */
+    PCR_ERR_BUSY = -4,    /* context used concurrently */
+    PCR_ERR_TOO_LARGE = -5 /* voxel/search grid would exceed the dense-grid cell budget */
+} pcr_status;
+
+typedef struct pcr_ctx pcr_ctx;
+
+/* open3d RegistrationResult as plain data (src/matcher/ransac.py:134-136, benchmark_ransac.py:199-200) */
+typedef struct pcr_reg_result {
+    double transformation[16];
+    double fitness;
+    double inlier_rmse;
+    int64_t inlier_count;
+    int64_t sum_d2_fixed; /* sum of llrint(d2 * 2^k_d) over inliers (determinism rule D5) */
+    int32_t k_d;
+    int32_t iterations;   /* ICP: update steps applied; RANSAC: unused */
+    int32_t converged;    /* ICP: 1 when the relative criteria stopped the loop */
+    int32_t reserved;
+    int64_t best_hyp;      /* RANSAC: global index of the winning hypothesis (-1: none) */
+    int64_t hyp_evaluated; /* RANSAC: hypotheses consumed by the sequential-equivalent loop */
+    int64_t survivors;     /* RANSAC: of those, how many passed both checkers */
+    int64_t est_k;         /* RANSAC: final early-exit bound */
+} pcr_reg_result;
+
+/* one scored RANSAC hypothesis (a survivor of both checkers) */
+typedef struct pcr_hyp_record {
+    int64_t hyp;          /* global hypothesis index */
+    int64_t inlier_count; /* source points with a target neighbour closer than max_dist */
+    int64_t sum_d2_fixed;
+    int32_t corr_inliers; /* correspondences with ||T s - t|| < max_dist (drives est_k) */
+    int32_t reserved;
+    double transformation[12]; /* rows 0..2 of the 4x4 */
+} pcr_hyp_record;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+PCR_API int pcr_create(int device, pcr_ctx **out);
+PCR_API int pcr_destroy(pcr_ctx *ctx);
+PCR_API const char *pcr_last_error(pcr_ctx *ctx);
+PCR_API int pcr_set_stream(pcr_ctx *ctx, void *cuda_stream);
+PCR_API int pcr_version(void);
+/* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
+PCR_API int64_t pcr_launch_count(pcr_ctx *ctx);
+
+/* ---- layout helpers ------------------------------------------------------------------------------- */
+/* (n,3) fp32 or fp64 device array -> packed float4 cloud (quantisation to fp32, rule D1) */
+PCR_API int pcr_pack_xyz_f32(pcr_ctx *ctx, const float *xyz_dev, int n, float *xyzw_dev);
+PCR_API int pcr_pack_xyz_f64(pcr_ctx *ctx, const double *xyz_dev, int n, float *xyzw_dev);
+PCR_API int pcr_unpack_xyz_f32(pcr_ctx *ctx, const float *xyzw_dev, int n, float *xyz_dev);
+
+/* ---- preprocessing (Ply._preprocess, src/ply/ply.py:87-135) ---------------------------------------- */
+/* pcd.voxel_down_sample(voxel)            src/ply/ply.py:106.  out_xyzw_dev capacity n; *m_host = #voxels */
+PCR_API int pcr_voxel_downsample(pcr_ctx *ctx, const float *xyzw_dev, int n, double voxel, float *out_xyzw_dev,
+                                 int *m_host);
+/* pcd.estimate_normals(KDTreeSearchParamHybrid(radius, max_nn))   src/ply/ply.py:110-112, 133-135 */
+PCR_API int pcr_estimate_normals(pcr_ctx *ctx, const float *xyzw_dev, int n, double radius, int max_nn,
+                                 float *normals_xyzw_dev);
+/* compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn))   src/ply/ply.py:117-120 */
+PCR_API int pcr_compute_fpfh(pcr_ctx *ctx, const float *xyzw_dev, const float *normals_xyzw_dev, int n, double radius,
+                             int max_nn, float *fpfh_dev /* n x 33 */);
+/* KDTreeFlann.search_hybrid_vector_3d for every query (diagnostic / tests): idx, d2 are (nq, max_nn) */
+PCR_API int pcr_knn_hybrid(pcr_ctx *ctx, const float *xyzw_dev, int n, const float *queries_xyzw_dev, int nq,
+                           double radius, int max_nn, int *idx_dev, float *d2_dev, int *cnt_dev);
+/* radius-limited 1-NN (the primitive inside registration_icp / RANSAC validation) */
+PCR_API int pcr_nn1(pcr_ctx *ctx, const float *tgt_xyzw_dev, int nt, const float *queries_xyzw_dev, int nq,
+                    double radius, int *idx_dev, float *d2_dev);
+
+/* ---- feature matching ----------------------------------------------------------------------------------- */
+/* correspondences_from_features(src_fpfh, tgt_fpfh, mutual_filter)   src/matcher/ransac.py:85 (and the
+ * matching stage inside registration_ransac_based_on_feature_matching, src/matcher/ransac.py:42-47).
+ * corr_dev capacity (ms, 2) int32; *c_host = number of pairs. */
+PCR_API int pcr_match_features(pcr_ctx *ctx, const float *fs_dev, int ms, const float *ft_dev, int mt, int mutual,
+                               double mutual_ratio, int *corr_dev, int *c_host);
+/* one-directional exact 33-D 1-NN (nn_dev[i] = argmin_j ||fq_i - fb_j||, ties -> lowest j) */
+PCR_API int pcr_nn_features(pcr_ctx *ctx, const float *fq_dev, int nq, const float *fb_dev, int nb, int *nn_dev);
+
+/* ---- RANSAC (registration_ransac_based_on_feature_matching, src/matcher/ransac.py:42-59) ---------------- */
+/* Full single-GPU loop over hypotheses [0, max_iter) with the sequential-equivalent early exit. */
+PCR_API int pcr_ransac(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                       const int *corr_dev, int c, double max_dist, double edge_sim, int64_t max_iter,
+                       double confidence, uint64_t seed, pcr_reg_result *result_host);
+/* One wave: score hypotheses [hyp_begin, hyp_end) and return the survivors that are prefix-maxima of this
+ * range — a superset: every survivor better than the running best (best_count, best_sum_d2_fixed; pass 0,0
+ * at the start), sorted by hypothesis index — to records_host (capacity cap; PCR_ERR_INVALID if it does not
+ * fit); *n_records_host = how many; *n_survivors_host = survivors in the range.
+ * Used by the multi-GPU driver: each rank scores its slice, records are all-gathered, pcr_ransac_scan merges. */
+PCR_API int pcr_ransac_wave(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                            const int *corr_dev, int c, double max_dist, double edge_sim, int64_t hyp_begin,
+                            int64_t hyp_end, uint64_t seed, int64_t best_count, int64_t best_sum_d2_fixed,
+                            pcr_hyp_record *records_host, int cap, int *n_records_host,
+                            int64_t *n_survivors_host);
+/* Host-only: replay the sequential loop over records sorted by hypothesis index, updating *state.
+ * Returns 1 in *stop_host when the early-exit bound was reached inside [hyp_begin, hyp_end). */
+PCR_API int pcr_ransac_scan(const pcr_hyp_record *records_host, int n, int64_t hyp_begin, int64_t hyp_end, int c,
+                            int ms, double confidence, int32_t k_d, pcr_reg_result *state, int *stop_host);
+PCR_API int pcr_ransac_k_d(double max_dist, int ms);
+
+/* ---- manual-step twins (src/matcher/ransac.py:104-277) -------------------------------------------------- */
+/* compute_step_transformation for hypotheses [h_begin, h_begin + count): 3 distinct correspondences drawn by
+ * Philox(seed, h), Kabsch.  T_dev: count x 16 fp64. */
+PCR_API int pcr_ransac_step(pcr_ctx *ctx, const float *src_xyzw_dev, const float *tgt_xyzw_dev, const int *corr_dev,
+                            int c, uint64_t seed, int64_t h_begin, int count, double *T_dev);
+/* evaluate_inlier_ratio / _fast for `count` transforms over c correspondences.  squared != 0: test
+ * d^2 < thresh (the _fast variant), else ||.|| < thresh.  counts_dev: count int32 inlier counts. */
+PCR_API int pcr_inlier_count(pcr_ctx *ctx, const float *src_xyzw_dev, const float *tgt_xyzw_dev, const int *corr_dev,
+                             int c, const double *T_dev, int count, double thresh, int squared, int *counts_dev);
+
+/* ---- ICP (registration_icp + TransformationEstimationPointToPlane, src/matcher/icp.py:42-48) ------------- */
+/* corr_dev: optional (ns) int32, target index per source point or -1. */
+PCR_API int pcr_icp_point_to_plane(pcr_ctx *ctx, const float *src_xyzw_dev, int ns, const float *tgt_xyzw_dev,
+                                   const float *tgt_normals_xyzw_dev, int nt, double max_dist,
+                                   const double *init_host /* 16 */, int max_iter, double rel_fitness,
+                                   double rel_rmse, pcr_reg_result *result_host, int *corr_dev);
+
+/* ---- end-to-end (the north-star call: clouds + voxel size -> 4x4, fitness, inlier RMSE) ------------------ */
+typedef struct pcr_align_params {
+    double voxel_size;
+    int64_t ransac_max_iter; /* reference default 30 (src/matcher/ransac.py:24) */
+    double ransac_confidence; /* 0.999 (src/matcher/ransac.py:58) */
+    uint64_t seed;
+    int32_t icp_max_iter;     /* Open3D default 30 (src/matcher/icp.py:42-48 passes no criteria) */
+    double icp_rel_fitness;   /* 1e-6 */
+    double icp_rel_rmse;      /* 1e-6 */
+    int32_t source_normals;   /* 1: also estimate full-resolution source normals, as Ply.__init__ does */
+    int32_t reserved;
+} pcr_align_params;
+
+typedef struct pcr_align_result {
+    pcr_reg_result ransac;
+    pcr_reg_result icp;
+    int32_t n_src_down, n_tgt_down, n_corr, reserved;
+    float stage_ms[8]; /* voxel, normals_down, fpfh, match, ransac, normals_full, icp, total (device time) */
+} pcr_align_result;
+
+PCR_API void pcr_align_default_params(pcr_align_params *p);
+/* device-resident inputs (packed float4) */
+PCR_API int pcr_align(pcr_ctx *ctx, const float *src_xyzw_dev, int ns, const float *tgt_xyzw_dev, int nt,
+                      const pcr_align_params *p, pcr_align_result *result_host);
+/* host inputs: (n,3) fp32 host arrays; H2D copies, the full path and the D2H of the result are inside */
+PCR_API int pcr_align_host(pcr_ctx *ctx, const float *src_xyz_host, int ns, const float *tgt_xyz_host, int nt,
+                           const pcr_align_params *p, pcr_align_result *result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCR_H */
