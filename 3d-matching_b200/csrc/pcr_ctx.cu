@@ -142,6 +142,15 @@ __global__ void k_unpack_xyz(const float4 *__restrict__ in, int n, float *__rest
     }
 }
 
+struct Mat12 { double m[12]; };
+__global__ void k_transform_points(const float4 *__restrict__ in, int n, Mat12 T, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    const float3 q = xform_pt(T.m, p.x, p.y, p.z);
+    out[i] = make_float4(q.x, q.y, q.z, p.w);
+}
+
 int pcr_pack_impl(pcr_ctx *ctx, const float *xyz, int n, float4 *out) {
     if (n <= 0) return PCR_OK;
     k_pack_xyz<float><<<div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, out);
@@ -171,6 +180,16 @@ int pcr_unpack_xyz_f32(pcr_ctx *ctx, const float *xyzw, int n, float *xyz) {
     if (!ctx || n < 0) return PCR_ERR_INVALID;
     if (n == 0) return PCR_OK;
     k_unpack_xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>((const float4 *)xyzw, n, xyz);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+int pcr_transform_points(pcr_ctx *ctx, const float *xyzw, int n, const double *T, float *out) {
+    if (!ctx || n < 0 || !T) return PCR_ERR_INVALID;
+    if (n == 0) return PCR_OK;
+    Mat12 m;
+    for (int i = 0; i < 12; i++) m.m[i] = T[i];
+    k_transform_points<<<div_up(n, 256), 256, 0, ctx->stream>>>((const float4 *)xyzw, n, m, (float4 *)out);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());
     return PCR_OK;

@@ -81,7 +81,7 @@ class AlignResult(C.Structure):
 # every symbol include/pcr.h declares (tests/test_capi_exports.py checks the list against the header)
 EXPORTS = [
     "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_set_stream", "pcr_version", "pcr_launch_count",
-    "pcr_pack_xyz_f32", "pcr_pack_xyz_f64", "pcr_unpack_xyz_f32",
+    "pcr_pack_xyz_f32", "pcr_pack_xyz_f64", "pcr_unpack_xyz_f32", "pcr_transform_points",
     "pcr_voxel_downsample", "pcr_estimate_normals", "pcr_compute_fpfh", "pcr_knn_hybrid", "pcr_nn1",
     "pcr_match_features", "pcr_nn_features",
     "pcr_ransac", "pcr_ransac_wave", "pcr_ransac_scan", "pcr_ransac_k_d",

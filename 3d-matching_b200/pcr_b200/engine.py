@@ -107,6 +107,17 @@ class Engine:
             self._check(fn(self.ctx, _ptr(t), C.c_int(n), _ptr(out)))
         return out
 
+    def transform_points(self, xyzw: torch.Tensor, T) -> torch.Tensor:
+        """out = fp32(R p + t) in the specified fp64 operation order (rule D7)."""
+        self._need_xyzw(xyzw, "points")
+        T = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4))
+        out = torch.empty_like(xyzw)
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_transform_points(self.ctx, _ptr(xyzw), C.c_int(xyzw.shape[0]),
+                                                      T.ctypes.data_as(C.c_void_p), _ptr(out)))
+        return out
+
     @staticmethod
     def _need_xyzw(t: torch.Tensor, name: str):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.ndim == 2

@@ -87,6 +87,10 @@ PCR_API int64_t pcr_launch_count(pcr_ctx *ctx);
 PCR_API int pcr_pack_xyz_f32(pcr_ctx *ctx, const float *xyz_dev, int n, float *xyzw_dev);
 PCR_API int pcr_pack_xyz_f64(pcr_ctx *ctx, const double *xyz_dev, int n, float *xyzw_dev);
 PCR_API int pcr_unpack_xyz_f32(pcr_ctx *ctx, const float *xyzw_dev, int n, float *xyz_dev);
+/* pcd.transform(T): out = fp32(R p + t) with the specified fp64 operation order (rule D7); in-place allowed.
+ * Used for RegistrationResult.correspondence_set and by _visualize_matcher.py:502-503-style callers. */
+PCR_API int pcr_transform_points(pcr_ctx *ctx, const float *xyzw_dev, int n, const double *T_host /* 16 */,
+                                 float *out_xyzw_dev);
 
 /* ---- preprocessing (Ply._preprocess, src/ply/ply.py:87-135) ---------------------------------------- */
 /* pcd.voxel_down_sample(voxel)            src/ply/ply.py:106.  out_xyzw_dev capacity n; *m_host = #voxels */

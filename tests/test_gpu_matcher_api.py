@@ -1,0 +1,148 @@
+"""The reference-facing Python surface (matcher.ransac / matcher.icp / ply.Ply) on the GPU: same names, positional
+order and soft-failure behaviour as src/matcher/*.py and src/ply/ply.py — the cases of the reference's own
+test_ransac_crash.py, with assertions."""
+import numpy as np
+import pytest
+
+from pcr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+class Cloud:
+    def __init__(self, pts):
+        self.points = np.asarray(pts, np.float64)
+
+
+class MockPly:  # test_ransac_crash.py:92-96
+    def __init__(self, pts):
+        self.pcd = Cloud(pts)
+        self.pcd_down = Cloud(pts)
+        self.pcd_fpfh = None
+
+
+def test_minimal_and_degenerate_correspondences(eng):
+    from matcher.ransac import compute_step_transformation, evaluate_inlier_ratio, evaluate_inlier_ratio_fast
+    rng = np.random.default_rng(0)
+    a, b = MockPly(rng.random((3, 3))), MockPly(rng.random((3, 3)))
+    r = compute_step_transformation(a, b, np.array([[0, 0], [1, 1], [2, 2]]))
+    assert r and r.fitness == 0.0 and np.isfinite(r.transformation).all()
+    col = np.array([[0, 0, i] for i in range(10)], float)
+    ident = np.stack([np.arange(10), np.arange(10)], 1)
+    assert np.array_equal(compute_step_transformation(MockPly(col), MockPly(col), ident).transformation, np.eye(4))
+    dup = np.array([[1, 1, 1]] * 10, float)
+    assert np.array_equal(compute_step_transformation(MockPly(dup), MockPly(dup), ident).transformation, np.eye(4))
+    cop = rng.random((10, 3)); cop[:, 2] = 0
+    assert np.isfinite(compute_step_transformation(MockPly(cop), MockPly(cop), ident).transformation).all()
+    r = compute_step_transformation(MockPly(col), MockPly(col), ident[:2])        # < 3 pairs (ransac.py:138-140)
+    assert np.array_equal(r.transformation, np.eye(4)) and r.fitness == 0.0
+    assert evaluate_inlier_ratio(a, b, np.zeros((0, 2), np.int32), np.eye(4), 0.05) == 0.0   # ransac.py:220-221
+    assert evaluate_inlier_ratio_fast(np.zeros((0, 3)), np.zeros((0, 3)), np.eye(4), 0.01) == 0.0
+    big = np.eye(4) * 1000.0; big[3, 3] = 1
+    pts = rng.random((50, 3))
+    cc = np.stack([np.arange(50), np.arange(50)], 1)
+    assert evaluate_inlier_ratio(MockPly(pts), MockPly(pts), cc, big, 0.05) < 0.1        # huge transform scores ~0
+    assert evaluate_inlier_ratio(MockPly(pts), MockPly(pts), cc, np.eye(4), 0.05) == 1.0
+    assert evaluate_inlier_ratio_fast(pts, pts, np.eye(4), 1e-6) == 1.0
+    for _ in range(200):  # stability: never NaN/Inf (test_ransac_crash.py:227-271)
+        assert np.isfinite(compute_step_transformation(MockPly(pts), MockPly(pts), cc).transformation).all()
+
+
+def test_ply_pipeline_and_main_style_calls(tmp_path, orc, eng):
+    from matcher.icp import refine_registration
+    from matcher.ransac import (compute_feature_correspondences, compute_step_transformations, evaluate_inlier_ratios,
+                                global_registration)
+    from pcr_b200.plyio import write_ply
+    from ply import Ply
+    v = 0.005
+    src, tgt, T = synth.make_pair(20000, v, 31)
+    write_ply(tmp_path / "sample.ply", src, binary=False)   # the reference's converter emits ASCII PLY
+    write_ply(tmp_path / "target.ply", tgt, binary=True)
+    with pytest.raises(FileNotFoundError):
+        Ply(tmp_path / "nope.ply")
+    (tmp_path / "x.txt").write_text("x")
+    with pytest.raises(TypeError):
+        Ply(tmp_path / "x.txt")
+    write_ply(tmp_path / "empty.ply", src[:0])
+    with pytest.raises(ValueError):
+        Ply(tmp_path / "empty.ply")
+    s = Ply(tmp_path / "sample.ply", v, noise_sigma=0.0)
+    t = Ply(tmp_path / "target.ply", v, noise_sigma=0.0)
+    assert s.voxel_size == v and len(s.pcd.points) == 20000 and s.pcd_fpfh.data.shape[0] == 33
+    So, To = orc.preprocess(src, v), orc.preprocess(tgt, v)
+    assert np.array_equal(s.pcd_down.points.astype(np.float32), So.pcd_down)
+    assert np.array_equal(s.pcd_fpfh.data.T.astype(np.float32), So.pcd_fpfh)
+    # global_registration(src, tgt, voxel_size, iteration) — reference positional order (ransac.py:20-25)
+    res = global_registration(s, t, v, 100000)
+    want = orc.global_registration(So, To, v, 100000, 0.999, 0)
+    assert res and np.array_equal(res.transformation, want.transformation)
+    assert res.fitness == want.fitness and res.inlier_rmse == want.inlier_rmse
+    assert len(res.correspondence_set) == want.inlier_count
+    # src/main.py:34,38 call without voxel_size -> falls back to the Ply's own
+    assert np.array_equal(global_registration(s, t, iteration=100000).transformation, res.transformation)
+    icp = refine_registration(s, t, res.transformation, v)
+    wicp = orc.refine_registration(So, To, want.transformation, v)
+    assert np.array_equal(icp.transformation, wicp.transformation) and icp.fitness == wicp.fitness
+    assert np.array_equal(icp.correspondence_set[:, 1], wicp.correspondence[wicp.correspondence >= 0])
+    assert np.array_equal(refine_registration(s, t, res).transformation, icp.transformation)  # main.py:38 arity
+    icp50 = refine_registration(s, t, res.transformation, v, max_iteration=50, relative_fitness=0.0, relative_rmse=0.0)
+    assert icp50.info["iterations"] == 50
+    # correspondences with injected noise: (1 + ratio) * C rows (ransac.py:89-99)
+    c0 = compute_feature_correspondences(s, t)
+    assert np.array_equal(c0, orc.match_features(So.pcd_fpfh, To.pcd_fpfh, False))
+    for ratio in (1, 5):
+        c = compute_feature_correspondences(s, t, noise_ratio=ratio, seed=1)
+        assert len(c) == (1 + ratio) * len(c0) and c.dtype == np.int32
+    Ts = compute_step_transformations(s, t, c0, 256, seed=2)
+    ratios = evaluate_inlier_ratios(s, t, c0, Ts, v)
+    assert ratios.shape == (256,) and ratios.max() <= 1.0
+    # the noisy Ply default (sigma 0.05, ply.py:61-62) only moves pcd_down, not the descriptors
+    sn = Ply(tmp_path / "sample.ply", v, seed=3)
+    assert np.array_equal(sn.pcd_fpfh.data, s.pcd_fpfh.data) and not np.array_equal(sn.pcd_down.points, s.pcd_down.points)
+    # point-to-plane without target normals is an error, as in Open3D
+    with pytest.raises(RuntimeError):
+        refine_registration(MockPly(src), MockPly(tgt), np.eye(4), v)
+
+
+def test_full_size_properties_100k(orc, eng):
+    """BASELINE config 2 sizes: size-independent properties + oracle parity on the cheap stages."""
+    from pcr_b200 import align
+    v = 0.005
+    src, tgt, T = synth.make_pair(100000, v, 20242)
+    Tg, fit, rmse, info = align(src, tgt, v, ransac_iteration=100000, icp_max_iteration=50, seed=7, return_info=True)
+    assert fit > 0.95 and np.abs(Tg[:3, :3] - T[:3, :3]).max() < 1e-3
+    R = Tg[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-9) and abs(np.linalg.det(R) - 1) < 1e-9
+    # rigid-motion equivariance: moving the source by M changes the answer to T M^-1 (up to RANSAC/ICP noise)
+    M = np.eye(4); M[:3, :3] = synth.euler_zyx(0.4, 0.1, -0.3); M[:3, 3] = [0.01, -0.02, 0.03]
+    src2 = (src.astype(np.float64) @ M[:3, :3].T + M[:3, 3]).astype(np.float32)
+    T2, fit2, _ = align(src2, tgt, v, ransac_iteration=100000, icp_max_iteration=50, seed=7)
+    assert fit2 > 0.95 and np.abs(T2 @ M - Tg).max() < 1e-3
+    # oracle parity at full size for the bandwidth-bound stages
+    ds, dt = eng.pack(src), eng.pack(tgt)
+    assert np.array_equal(eng.voxel_downsample(ds, v)[:, :3].cpu().numpy(), orc.voxel_downsample(src, v))
+    otn = orc.estimate_normals(tgt, 2 * v, 30)
+    assert np.array_equal(eng.estimate_normals(dt, 2 * v, 30)[:, :3].cpu().numpy(), otn)
+    g, corr = eng.icp_point_to_plane(ds, dt, eng.pack(otn), 0.4 * v, Tg, 10, 0.0, 0.0)
+    o = orc.icp_point_to_plane(src, tgt, otn, 0.4 * v, Tg, 10, 0.0, 0.0)
+    assert np.array_equal(g.transformation, o.transformation) and np.array_equal(corr.cpu().numpy(), o.correspondence)
+
+
+def test_icp_1m_properties(eng):
+    """BASELINE config 3 size (1M points): every reported correspondence is a true radius-limited nearest neighbour."""
+    import torch
+    v = 0.005
+    src, tgt, T = synth.make_icp_pair(1000000, v, 20243)
+    ds, dt = eng.pack(src), eng.pack(tgt)
+    n = eng.estimate_normals(dt, 2 * v, 30)
+    g, corr = eng.icp_point_to_plane(ds, dt, n, 0.4 * v, np.eye(4), 50, 0.0, 0.0)
+    assert g.iterations == 50 and g.fitness > 0.9
+    assert g.inlier_count == int((corr >= 0).sum())
+    moved = eng.transform_points(ds, g.transformation)
+    idx, d2 = eng.nn1(dt, moved, 0.4 * v)
+    assert torch.equal(idx, corr)
+    sel = torch.nonzero(corr >= 0)[:200000, 0]
+    d = (moved[sel, :3] - dt[corr[sel].long(), :3]).double().norm(dim=1)
+    assert float(d.max()) < 0.4 * v * (1 + 1e-6)
+    assert abs(g.inlier_rmse - float(torch.sqrt((d2[corr >= 0].double()).mean()))) < 1e-9
+    assert np.abs(g.transformation - T).max() < 5e-5

@@ -1,0 +1,261 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (pcr_b200.engine -> libpcr_b200.so), against
+the CPU oracle on the same seeded inputs.  Bit-exact for every integer output (voxel assignment, neighbour
+indices, correspondences, inlier counts, winning hypothesis) and — because the arithmetic specification is
+shared — for the floating-point outputs as well; the north-star tolerance (1e-5 rotation,
+1e-5 * extent translation) is asserted separately where a looser bound is the contract."""
+import numpy as np
+import pytest
+import torch
+
+from pcr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def xyz(t):
+    return t[:, :3].cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def pair(orc, eng):
+    v = 0.005
+    src, tgt, T = synth.make_pair(20000, v, 20241)
+    d = {"v": v, "src": src, "tgt": tgt, "T": T, "ds": eng.pack(src), "dt": eng.pack(tgt)}
+    d["osd"], d["otd"] = orc.voxel_downsample(src, v), orc.voxel_downsample(tgt, v)
+    d["osn"], d["otn"] = orc.estimate_normals(d["osd"], 2 * v, 30), orc.estimate_normals(d["otd"], 2 * v, 30)
+    d["osf"], d["otf"] = orc.fpfh(d["osd"], d["osn"], 5 * v, 100), orc.fpfh(d["otd"], d["otn"], 5 * v, 100)
+    d["ocorr"] = orc.match_features(d["osf"], d["otf"], True)
+    d["sd"], d["td"] = eng.voxel_downsample(d["ds"], v).contiguous(), eng.voxel_downsample(d["dt"], v).contiguous()
+    d["sn"], d["tn"] = eng.estimate_normals(d["sd"], 2 * v, 30), eng.estimate_normals(d["td"], 2 * v, 30)
+    d["sf"], d["tf"] = eng.compute_fpfh(d["sd"], d["sn"], 5 * v, 100), eng.compute_fpfh(d["td"], d["tn"], 5 * v, 100)
+    d["corr"] = eng.match_features(d["sf"], d["tf"], True).contiguous()
+    return d
+
+
+def test_pack_quantises_fp64(eng):
+    a = np.random.default_rng(0).normal(size=(1000, 3))
+    t = eng.pack(a)
+    assert np.array_equal(xyz(t), a.astype(np.float32)) and torch.all(t[:, 3] == 0)
+    assert eng.pack(np.zeros((0, 3))).shape == (0, 4)
+
+
+def test_voxel_downsample(pair):
+    assert np.array_equal(xyz(pair["sd"]), pair["osd"]) and np.array_equal(xyz(pair["td"]), pair["otd"])
+
+
+@pytest.mark.parametrize("voxel", [0.002, 0.01, 0.05, 1.0])
+def test_voxel_sizes(orc, eng, pair, voxel):
+    assert np.array_equal(xyz(eng.voxel_downsample(pair["ds"], voxel)), orc.voxel_downsample(pair["src"], voxel))
+
+
+def test_voxel_edge_cases(orc, eng):
+    with pytest.raises(ValueError):
+        eng.voxel_downsample(eng.pack(np.zeros((5, 3))), 0.0)
+    assert eng.voxel_downsample(eng.pack(np.zeros((0, 3))), 0.3).shape[0] == 0
+    dup = np.ones((10, 3), np.float32)
+    assert np.array_equal(xyz(eng.voxel_downsample(eng.pack(dup), 0.3)), orc.voxel_downsample(dup, 0.3))
+    one = np.array([[1.5, -2.0, 3.25]], np.float32)
+    assert np.array_equal(xyz(eng.voxel_downsample(eng.pack(one), 0.3)), one)
+    with pytest.raises(ValueError):  # dense voxel grid budget (PCR_ERR_TOO_LARGE)
+        eng.voxel_downsample(eng.pack(np.array([[0, 0, 0], [1e3, 1e3, 1e3]], np.float32)), 1e-3)
+
+
+@pytest.mark.parametrize("radius_v,k", [(2, 30), (5, 100), (1.2, 4), (8, 256)])
+def test_knn_hybrid(orc, eng, pair, radius_v, k):
+    v = pair["v"]
+    q = pair["ds"][:3000].contiguous()
+    idx, d2, cnt = eng.knn_hybrid(pair["ds"], q, radius_v * v, k)
+    oi, od, oc = orc.knn_hybrid(pair["src"], pair["src"][:3000], radius_v * v, k)
+    assert np.array_equal(cnt.cpu().numpy(), oc)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(d2.cpu().numpy(), od)
+
+
+def test_knn_ties_duplicates_and_outside_queries(orc, eng):
+    rng = np.random.default_rng(3)
+    lat = (rng.integers(0, 5, (800, 3)) * 0.25).astype(np.float32)  # many exact ties and duplicate points
+    q = np.concatenate([lat[:100], rng.uniform(-3, 4, (100, 3)).astype(np.float32)])
+    idx, d2, cnt = eng.knn_hybrid(eng.pack(lat), eng.pack(q), 0.6, 40)
+    oi, od, oc = orc.knn_hybrid(lat, q, 0.6, 40)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od) and np.array_equal(cnt.cpu().numpy(), oc)
+    # buffer overflow path: > 1024 in-radius candidates per query
+    dense = rng.normal(0, 0.05, (5000, 3)).astype(np.float32)
+    idx, d2, cnt = eng.knn_hybrid(eng.pack(dense), eng.pack(dense[:200]), 0.2, 50)
+    oi, od, oc = orc.knn_hybrid(dense, dense[:200], 0.2, 50)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od)
+    # empty index
+    idx, d2, cnt = eng.knn_hybrid(eng.pack(np.zeros((0, 3))), eng.pack(q), 0.5, 5)
+    assert torch.all(idx == -1) and torch.all(cnt == 0)
+
+
+def test_nn1(orc, eng, pair):
+    v = pair["v"]
+    moved = orc.transform_points(pair["T"], pair["src"])
+    idx, d2 = eng.nn1(pair["dt"], eng.pack(moved), 0.4 * v)
+    oi, od = orc.nn1(pair["tgt"], moved, 0.4 * v)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od)
+    tgt = np.array([[0, 0, 0], [1, 0, 0]], np.float32)
+    q = np.array([[0.5, 0, 0], [3, 0, 0], [0.25, 0, 0]], np.float32)
+    assert eng.nn1(eng.pack(tgt), eng.pack(q), 0.5)[0].tolist() == [-1, -1, 0]       # strict radius
+    assert eng.nn1(eng.pack(tgt), eng.pack(q), 0.5000001)[0].tolist() == [0, -1, 0]  # tie -> lowest index
+    with pytest.raises(ValueError):
+        eng.nn1(eng.pack(tgt), eng.pack(q), 0.0)
+
+
+def test_transform_points(orc, eng, pair):
+    assert np.array_equal(xyz(eng.transform_points(pair["ds"], pair["T"])), orc.transform_points(pair["T"], pair["src"]))
+
+
+def test_normals(orc, eng, pair):
+    assert np.array_equal(xyz(pair["sn"]), pair["osn"]) and np.array_equal(xyz(pair["tn"]), pair["otn"])
+    full = eng.estimate_normals(pair["dt"], 2 * pair["v"], 30)
+    assert np.array_equal(xyz(full), orc.estimate_normals(pair["tgt"], 2 * pair["v"], 30))
+    lonely = np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0]], np.float32)
+    assert np.array_equal(xyz(eng.estimate_normals(eng.pack(lonely), 0.5, 30)), [[0, 0, 1]] * 3)
+    plane = np.concatenate([np.random.default_rng(0).uniform(-1, 1, (2000, 2)), np.zeros((2000, 1))], 1).astype(np.float32)
+    assert np.array_equal(xyz(eng.estimate_normals(eng.pack(plane), 0.2, 30)), orc.estimate_normals(plane, 0.2, 30))
+
+
+def test_fpfh(orc, eng, pair):
+    assert np.array_equal(pair["sf"].cpu().numpy(), pair["osf"]) and np.array_equal(pair["tf"].cpu().numpy(), pair["otf"])
+    lonely = np.array([[0, 0, 0], [50, 0, 0]], np.float32)
+    nrm = np.array([[0, 0, 1], [0, 0, 1]], np.float32)
+    assert torch.all(eng.compute_fpfh(eng.pack(lonely), eng.pack(nrm), 1.0, 100) == 0)
+
+
+def test_feature_matching(orc, eng, pair):
+    assert np.array_equal(pair["corr"].cpu().numpy(), pair["ocorr"])
+    one = eng.match_features(pair["sf"], pair["tf"], False)
+    assert np.array_equal(one.cpu().numpy(), orc.match_features(pair["osf"], pair["otf"], False))
+    assert np.array_equal(eng.nn_features(pair["tf"], pair["sf"]).cpu().numpy(), orc.nn_features(pair["otf"], pair["osf"]))
+    # fall-back when too few mutual pairs; exact ties and all-zero descriptors
+    rng = np.random.default_rng(11)
+    fs = rng.uniform(0, 200, (300, 33)).astype(np.float32)
+    ft = rng.uniform(0, 200, (260, 33)).astype(np.float32)
+    ft[10] = fs[3]; ft[20] = fs[3]; fs[50] = 0; ft[60] = 0; ft[70] = 0
+    dfs, dft = torch.from_numpy(fs).cuda(), torch.from_numpy(ft).cuda()
+    for mutual, ratio in ((False, 0.1), (True, 0.0), (True, 0.1), (True, 0.99)):
+        assert np.array_equal(eng.match_features(dfs, dft, mutual, ratio).cpu().numpy(), orc.match_features(fs, ft, mutual, ratio))
+    assert eng.match_features(dfs[:0].contiguous(), dft, True).shape[0] == 0
+
+
+@pytest.mark.parametrize("conf,iters,seed", [(0.999, 100000, 1), (0.999, 100000, 2), (1.0, 6000, 3), (0.9, 50, 4)])
+def test_ransac(orc, eng, pair, conf, iters, seed):
+    v = pair["v"]
+    r = eng.ransac(pair["sd"], pair["td"], pair["corr"], 1.5 * v, iters, conf, seed)
+    o = orc.ransac(pair["osd"], pair["otd"], pair["ocorr"], 1.5 * v, iters, conf, seed)
+    assert (r.best_hyp, r.inlier_count, r.sum_d2_fixed, r.est_k, r.hyp_evaluated) == \
+           (o.best_hyp, o.inlier_count, o.sum_d2_fixed, o.est_k, o.hyp_evaluated)
+    assert np.array_equal(r.transformation, o.transformation)
+    assert r.fitness == o.fitness and r.inlier_rmse == o.inlier_rmse
+    if conf == 1.0:
+        assert r.survivors == o.survivors
+
+
+def test_ransac_waves_match_single_call(orc, eng, pair):
+    """pcr_ransac_wave + pcr_ransac_scan (the multi-GPU building blocks) on one GPU, emulating 3 ranks."""
+    from pcr_b200.dist import ransac_distributed, records_to_array
+    import ctypes as C
+    v = pair["v"]
+    k_d = int(eng.lib.pcr_ransac_k_d(C.c_double(1.5 * v), C.c_int(pair["sd"].shape[0])))
+
+    def wave_fn(lo, hi, bc, bs):
+        parts, ns = [], 0
+        for r in range(3):  # three emulated ranks, concatenated in rank order
+            a = lo + (hi - lo) * r // 3
+            b = lo + (hi - lo) * (r + 1) // 3
+            if b > a:
+                recs, n, s = eng.ransac_wave(pair["sd"], pair["td"], pair["corr"], 1.5 * v, a, b, 5, 0.9, 4096, bc, bs)
+                parts.append(records_to_array(recs, n)); ns += s
+        return (np.concatenate(parts) if parts else np.zeros((0, 16), np.int64)), ns
+    st, _ = ransac_distributed(wave_fn, pair["corr"].shape[0], pair["sd"].shape[0], k_d, 100000, 0.999, lib=eng.lib, first_wave=1000)
+    o = orc.ransac(pair["osd"], pair["otd"], pair["ocorr"], 1.5 * v, 100000, 0.999, 5)
+    assert (st.best_hyp, st.inlier_count, st.sum_d2_fixed, st.est_k, st.hyp_evaluated) == \
+           (o.best_hyp, o.inlier_count, o.sum_d2_fixed, o.est_k, o.hyp_evaluated)
+    assert np.array_equal(np.array(st.transformation).reshape(4, 4), o.transformation)
+
+
+def test_ransac_degenerate(eng, pair):
+    v = pair["v"]
+    r = eng.ransac(pair["sd"], pair["td"], pair["corr"][:2].contiguous(), 1.5 * v, 100)
+    assert r.best_hyp == -1 and r.fitness == 0 and np.array_equal(r.transformation, np.eye(4))
+    r = eng.ransac(pair["sd"], pair["td"], pair["corr"], 0.0, 100)
+    assert r.best_hyp == -1
+
+
+def test_manual_step_twins(orc, eng, pair):
+    v = pair["v"]
+    Ts = eng.ransac_step(pair["sd"], pair["td"], pair["corr"], 9, 100, 512)
+    cnt = eng.inlier_count(pair["sd"], pair["td"], pair["corr"], Ts, 1.5 * v).cpu().numpy()
+    cnt2 = eng.inlier_count(pair["sd"], pair["td"], pair["corr"], Ts, (1.5 * v) ** 2, squared=True).cpu().numpy()
+    Tn = Ts.cpu().numpy()
+    for i in range(0, 512, 37):
+        oT, _ = orc.ransac_step(pair["osd"], pair["otd"], pair["ocorr"], 9, 100 + i)
+        assert np.array_equal(Tn[i], oT)
+        assert cnt[i] == orc.inlier_count(pair["osd"], pair["otd"], pair["ocorr"], oT, 1.5 * v)
+        assert cnt2[i] == orc.inlier_count(pair["osd"], pair["otd"], pair["ocorr"], oT, (1.5 * v) ** 2, squared=True)
+
+
+def test_device_kabsch_against_reference_golden(eng):
+    """Three correspondences -> the sample is all of them: compare with the reference's NumPy Kabsch output."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_numpy_golden.npz"))
+    checked = 0
+    for k in range(int(g["n_cases"])):
+        src, tgt, corr, idx, T = g[f"src_{k}"], g[f"tgt_{k}"], g[f"corr_{k}"], g[f"idx_{k}"], g[f"T_{k}"]
+        c3 = np.ascontiguousarray(corr[idx])
+        s3, t3 = src[c3[:, 0]].astype(np.float64), tgt[c3[:, 1]].astype(np.float64)
+        sv = np.linalg.svd((s3 - s3.mean(0)).T @ (t3 - t3.mean(0)), compute_uv=False)
+        if sv[1] <= 1e-3 * sv[0]:
+            continue
+        mine = eng.ransac_step(eng.pack(src), eng.pack(tgt), torch.from_numpy(c3).cuda(), 0, 0, 1)[0].cpu().numpy()
+        assert np.abs(mine[:3, :3] - T[:3, :3]).max() < 1e-5          # north-star rotation tolerance
+        assert np.abs(mine[:3, 3] - T[:3, 3]).max() < 1e-5 * 4.0      # 1e-5 * extent
+        assert np.abs(mine - T).max() < 1e-7                           # what is actually achieved
+        checked += 1
+    assert checked >= 12
+
+
+@pytest.mark.parametrize("iters,rf,rr", [(30, 1e-6, 1e-6), (12, 0.0, 0.0), (0, 1e-6, 1e-6)])
+def test_icp(orc, eng, pair, iters, rf, rr):
+    v = pair["v"]
+    pert = np.eye(4); pert[:3, :3] = synth.euler_zyx(0.002, -0.001, 0.0015); pert[:3, 3] = [2e-4, -3e-4, 1e-4]
+    init = pert @ pair["T"]
+    otn = orc.estimate_normals(pair["tgt"], 2 * v, 30)
+    g, corr = eng.icp_point_to_plane(pair["ds"], pair["dt"], eng.pack(otn), 0.4 * v, init, iters, rf, rr)
+    o = orc.icp_point_to_plane(pair["src"], pair["tgt"], otn, 0.4 * v, init, iters, rf, rr)
+    assert np.array_equal(corr.cpu().numpy(), o.correspondence)
+    assert (g.inlier_count, g.sum_d2_fixed, g.iterations, g.converged) == (o.inlier_count, o.sum_d2_fixed, o.iterations, o.converged)
+    assert np.array_equal(g.transformation, o.transformation)
+    assert g.fitness == o.fitness and g.inlier_rmse == o.inlier_rmse
+
+
+def test_icp_edge_cases(eng, pair):
+    v = pair["v"]
+    n = eng.pack(np.tile([[0, 0, 1.0]], (pair["dt"].shape[0], 1)))
+    with pytest.raises(ValueError):
+        eng.icp_point_to_plane(pair["ds"], pair["dt"], n, 0.0)
+    far = np.eye(4); far[:3, 3] = 100.0  # no correspondences at all: identity updates, fitness 0
+    g, corr = eng.icp_point_to_plane(pair["ds"], pair["dt"], n, 0.4 * v, far, 5)
+    assert g.fitness == 0 and g.inlier_count == 0 and torch.all(corr == -1) and np.array_equal(g.transformation, far)
+    empty = eng.pack(np.zeros((0, 3)))
+    g, corr = eng.icp_point_to_plane(empty, pair["dt"], n, 0.4 * v)
+    assert g.fitness == 0 and corr.shape[0] == 0
+
+
+def test_align_end_to_end(orc, eng, pair):
+    from pcr_b200 import align
+    v = pair["v"]
+    T, fit, rmse, info = align(pair["src"], pair["tgt"], v, ransac_iteration=100000, seed=1, return_info=True)
+    S, G = orc.preprocess(pair["src"], v), orc.preprocess(pair["tgt"], v)
+    ro = orc.global_registration(S, G, v, 100000, 0.999, 1)
+    io = orc.refine_registration(S, G, ro.transformation, v)
+    assert np.array_equal(T, io.transformation) and fit == io.fitness and rmse == io.inlier_rmse
+    assert info.ransac.best_hyp == ro.best_hyp and info.n_corr == len(pair["ocorr"])
+    # recovers the known SE(3): 1e-5-level agreement is with the oracle; vs ground truth it is the sampling noise
+    assert np.abs(T[:3, :3] - pair["T"][:3, :3]).max() < 2e-3 and fit > 0.95
+    # device-resident inputs give the same bits; the call is deterministic run to run
+    T2, fit2, rmse2 = align(pair["ds"], pair["dt"], v, ransac_iteration=100000, seed=1)
+    assert np.array_equal(T, T2) and fit == fit2 and rmse == rmse2
+    with pytest.raises(ValueError):
+        align(np.zeros((0, 3)), pair["tgt"], v)
