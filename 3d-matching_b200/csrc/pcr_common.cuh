@@ -16,7 +16,28 @@
 
 #define PCR_MAX_GRID_CELLS (1LL << 27)
 
+// kernel classes for the optional per-kernel timing (pcr_set_profiling / pcr_kernel_stats)
+enum KClass {
+    KC_PACK = 0, KC_BOUNDS, KC_GRID_BUILD, KC_SCAN, KC_VOXEL, KC_KNN_LIST, KC_KNN_COV, KC_NORMALS_SOLVE, KC_SPFH, KC_FPFH,
+    KC_NN_FEATURES, KC_MATCH_MISC, KC_RANSAC_GENERATE, KC_RANSAC_VALIDATE, KC_RANSAC_STEP, KC_ICP_PASS, KC_NN1, KC_COUNT
+};
+
+struct KPending {
+    int id;
+    cudaEvent_t a, b;
+    double bytes;   // algorithmic bytes per launch
+    double flops;   // algorithmic flops per launch (descriptor GEMM only)
+    long long launches;
+};
+
 struct pcr_ctx {
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<KPending> pending;
+    double k_ms[KC_COUNT] = {0};
+    double k_bytes[KC_COUNT] = {0};
+    double k_flops[KC_COUNT] = {0};
+    long long k_launches[KC_COUNT] = {0};
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -33,6 +54,17 @@ struct pcr_ctx {
 
 extern std::atomic<long long> g_pcr_launches;
 #define PCR_LAUNCHED() (g_pcr_launches++)
+
+// RAII scope: when profiling is on, brackets the kernels launched inside it with a CUDA event pair on the
+// context's stream; pcr_kernel_stats() later resolves the pairs.  `launches` kernels of the class are inside.
+struct KScope {
+    pcr_ctx *ctx;
+    KPending p;
+    bool on;
+    KScope(pcr_ctx *c, int id, double bytes_per_launch, long long launches = 1, double flops_per_launch = 0.0);
+    ~KScope();
+    void set_launches(long long n) { p.launches = n; }
+};
 
 // ---- error handling -------------------------------------------------------------------------------
 int pcr_fail(pcr_ctx *ctx, int code, const char *fmt, ...);

@@ -18,6 +18,37 @@ int pcr_fail(pcr_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+static cudaEvent_t ev_get(pcr_ctx *ctx) {
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+KScope::KScope(pcr_ctx *c, int id, double bytes_per_launch, long long launches, double flops_per_launch)
+    : ctx(c), on(c && c->profiling) {
+    p.id = id;
+    p.bytes = bytes_per_launch;
+    p.flops = flops_per_launch;
+    p.launches = launches;
+    if (on) {
+        p.a = ev_get(ctx);
+        p.b = ev_get(ctx);
+        cudaEventRecord(p.a, ctx->stream);
+    }
+}
+
+KScope::~KScope() {
+    if (on) {
+        cudaEventRecord(p.b, ctx->stream);
+        ctx->pending.push_back(p);
+    }
+}
+
 int pcr_pow2ceil_exp(double x) {
     int e;
     const double m = frexp(x, &e);
@@ -106,6 +137,8 @@ int pcr_destroy(pcr_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (void *b : ctx->blocks) cudaFree(b);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
     return PCR_OK;
@@ -122,6 +155,52 @@ int pcr_set_stream(pcr_ctx *ctx, void *cuda_stream) {
 int64_t pcr_launch_count(pcr_ctx *ctx) {
     (void)ctx;
     return g_pcr_launches.load();
+}
+
+int pcr_set_profiling(pcr_ctx *ctx, int enabled) {
+    if (!ctx) return PCR_ERR_INVALID;
+    ctx->profiling = enabled != 0;
+    return PCR_OK;
+}
+
+static const char *const KNAMES[KC_COUNT] = {
+    "pack", "bounds", "grid_build", "scan", "voxel", "knn_list", "knn_cov", "normals_solve", "spfh", "fpfh",
+    "nn_features", "match_misc", "ransac_generate", "ransac_validate", "ransac_step", "icp_pass", "nn1"};
+
+int pcr_kernel_class_count(void) { return KC_COUNT; }
+const char *pcr_kernel_class_name(int id) { return (id >= 0 && id < KC_COUNT) ? KNAMES[id] : ""; }
+
+int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset) {
+    if (!ctx || !out || cap < KC_COUNT) return PCR_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (const KPending &p : ctx->pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->k_ms[p.id] += ms;
+            ctx->k_launches[p.id] += p.launches;
+            ctx->k_bytes[p.id] += p.bytes * (double)p.launches;
+            ctx->k_flops[p.id] += p.flops * (double)p.launches;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+    for (int i = 0; i < KC_COUNT; i++) {
+        out[i].total_ms = ctx->k_ms[i];
+        out[i].launches = ctx->k_launches[i];
+        out[i].bytes = ctx->k_bytes[i];
+        out[i].flops = ctx->k_flops[i];
+        if (reset) {
+            ctx->k_ms[i] = 0;
+            ctx->k_launches[i] = 0;
+            ctx->k_bytes[i] = 0;
+            ctx->k_flops[i] = 0;
+        }
+    }
+    return PCR_OK;
 }
 
 }  // extern "C"

@@ -48,11 +48,14 @@ __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, 
 
 int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]) {
     PCR_ALLOC(b, int, 8);
+    {
+    KScope ks(ctx, KC_BOUNDS, 16.0 * n);
     k_bounds_init<<<1, 32, 0, ctx->stream>>>(b);
     PCR_LAUNCHED();
     const int blocks = min(div_up(n, 256), ctx->sm_count * 8);
     k_bounds<<<blocks, 256, 0, ctx->stream>>>(pts, n, b);
     PCR_LAUNCHED();
+    }
     int *hb = (int *)ctx->pinned;
     PCR_CUDA(cudaMemcpyAsync(hb, b, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -253,6 +256,7 @@ int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const 
     PCR_ALLOC(start, uint32_t, (size_t)ncells + 1);
     PCR_ALLOC(fill, uint32_t, (size_t)ncells);
     PCR_ALLOC(sorted, float4, (size_t)n);
+    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 16.0 * (double)ncells);
     PCR_CUDA(cudaMemsetAsync(start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), ctx->stream));
     PCR_CUDA(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)ncells, ctx->stream));
     k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, start);

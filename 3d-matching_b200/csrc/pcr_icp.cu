@@ -272,9 +272,13 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     const float r2 = (float)(max_dist * max_dist);
     const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * 8);
-    for (int pass = 0; pass <= max_iter; pass++) {
-        k_icp_pass<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, g, tgt, nrm, r2, dS, corr);
-        PCR_LAUNCHED();
+    const size_t pend_idx = ctx->pending.size();
+    {
+        KScope ks(ctx, KC_ICP_PASS, 16.0 * ns + 32.0 * nt + 4.0 * ns, max_iter + 1);
+        for (int pass = 0; pass <= max_iter; pass++) {
+            k_icp_pass<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, g, tgt, nrm, r2, dS, corr);
+            PCR_LAUNCHED();
+        }
     }
     PCR_CUDA(cudaGetLastError());
     PCR_CUDA(cudaMemcpyAsync(hS, dS, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -288,6 +292,8 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
         res->k_d = k_d;
         res->iterations = hS->iterations;
         res->converged = hS->converged;
+        // passes that did work (the rest returned at the `done` check): iterations + 1
+        if (ctx->profiling && pend_idx < ctx->pending.size()) ctx->pending[pend_idx].launches = hS->pass;
     }
     return PCR_OK;
 }
@@ -302,6 +308,7 @@ int pcr_nn1_impl(pcr_ctx *ctx, const float4 *tgt, int nt, const float4 *q, int n
     }
     Grid g;
     PCR_TRY(pcr_grid_build(ctx, tgt, nt, radius, nullptr, nullptr, &g));
+    KScope ks(ctx, KC_NN1, 16.0 * nt + 24.0 * nq);
     k_nn1<<<div_up(nq, 256), 256, 0, ctx->stream>>>(q, nq, g, (float)(radius * radius), idx, d2);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());

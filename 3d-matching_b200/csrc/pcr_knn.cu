@@ -408,6 +408,7 @@ int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq
     }
     Grid g;
     PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
+    KScope ks(ctx, KC_KNN_LIST, 16.0 * n + 16.0 * nq + 8.0 * (double)nq * max_nn);
     k_knn_list<<<knn_blocks(ctx, nq), KNN_WARPS * 32, 0, ctx->stream>>>(q, nq, g, (float)(radius * radius), max_nn, idx,
                                                                         d2, cnt);
     PCR_LAUNCHED();
@@ -422,11 +423,16 @@ int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int 
     Grid g;
     PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
     PCR_ALLOC(cov, double, (size_t)n * 6);
-    // queries are visited in cell-sorted order for locality: use the sorted copy as the query list
-    k_knn_cov<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
-    PCR_LAUNCHED();
-    k_normals_solve<<<div_up(n, 128), 128, 0, ctx->stream>>>(cov, n, normals);
-    PCR_LAUNCHED();
+    {
+        KScope ks(ctx, KC_KNN_COV, 32.0 * n + 48.0 * n);
+        k_knn_cov<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+        PCR_LAUNCHED();
+    }
+    {
+        KScope ks(ctx, KC_NORMALS_SOLVE, 48.0 * n + 16.0 * n);
+        k_normals_solve<<<div_up(n, 128), 128, 0, ctx->stream>>>(cov, n, normals);
+        PCR_LAUNCHED();
+    }
     PCR_CUDA(cudaGetLastError());
     return PCR_OK;
 }
@@ -441,14 +447,23 @@ int pcr_fpfh_impl(pcr_ctx *ctx, const float4 *pts, const float4 *nrm, int n, dou
     PCR_ALLOC(d2, float, (size_t)n * max_nn);
     PCR_ALLOC(cnt, int, (size_t)n);
     PCR_ALLOC(spfh, double, (size_t)n * 33);
-    k_knn_list<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, idx,
-                                                                       d2, cnt);
-    PCR_LAUNCHED();
+    {
+        KScope ks(ctx, KC_KNN_LIST, 32.0 * n + 8.0 * (double)n * max_nn);
+        k_knn_list<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn,
+                                                                           idx, d2, cnt);
+        PCR_LAUNCHED();
+    }
     const int blocks = min(div_up(n, 4), ctx->sm_count * 16);
-    k_spfh<<<blocks, 128, 0, ctx->stream>>>(pts, nrm, n, idx, cnt, max_nn, spfh);
-    PCR_LAUNCHED();
-    k_fpfh<<<blocks, 128, 0, ctx->stream>>>(n, idx, d2, cnt, max_nn, spfh, out);
-    PCR_LAUNCHED();
+    {
+        KScope ks(ctx, KC_SPFH, 32.0 * n + 4.0 * (double)n * max_nn + 264.0 * n);
+        k_spfh<<<blocks, 128, 0, ctx->stream>>>(pts, nrm, n, idx, cnt, max_nn, spfh);
+        PCR_LAUNCHED();
+    }
+    {
+        KScope ks(ctx, KC_FPFH, 264.0 * n + 8.0 * (double)n * max_nn + 132.0 * n);
+        k_fpfh<<<blocks, 128, 0, ctx->stream>>>(n, idx, d2, cnt, max_nn, spfh, out);
+        PCR_LAUNCHED();
+    }
     PCR_CUDA(cudaGetLastError());
     return PCR_OK;
 }

@@ -71,6 +71,7 @@ int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb,
         PCR_CUDA(cudaMemsetAsync(nn, 0xff, sizeof(int) * (size_t)nq, ctx->stream));
         return PCR_OK;
     }
+    KScope ks(ctx, KC_NN_FEATURES, 132.0 * ((double)nq + nb) + 4.0 * nq, 1, 2.0 * 33.0 * (double)nq * (double)nb);
     k_nn_features_exact<<<div_up(nq, NNF_THREADS), NNF_THREADS, 0, ctx->stream>>>(fq, nq, fb, nb, nn);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());

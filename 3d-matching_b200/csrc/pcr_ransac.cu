@@ -383,19 +383,29 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     PCR_ALLOC(counters, unsigned int, 4);
     PCR_ALLOC(recs, pcr_hyp_record, (size_t)cap);
     PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
-    k_ransac_generate<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, max_dist, edge_sim,
-                                                                   hyp_begin, count, seed, surv, counters);
-    PCR_LAUNCHED();
+    {
+        KScope ks(ctx, KC_RANSAC_GENERATE, 120.0 * (double)count);
+        k_ransac_generate<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, max_dist, edge_sim,
+                                                                       hyp_begin, count, seed, surv, counters);
+        PCR_LAUNCHED();
+    }
     const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * 8);
+    const size_t pend_idx = ctx->pending.size();
+    {
+    KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
     k_ransac_validate<<<vblocks, VAL_THREADS, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
                                                                 w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt,
                                                                 best_sumq, recs, counters + 1, (unsigned int)cap);
     PCR_LAUNCHED();
+    }
     PCR_CUDA(cudaGetLastError());
     unsigned int *hc = (unsigned int *)ctx->pinned;
     PCR_CUDA(cudaMemcpyAsync(hc, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     *n_surv_host = hc[0];
+    // algorithmic bytes of the validation launch: per survivor 16 M_s (source) + 16 M_t (target) + 8 C (pairs)
+    if (ctx->profiling && pend_idx < ctx->pending.size())
+        ctx->pending[pend_idx].bytes = (double)hc[0] * (16.0 * ms + 16.0 * w.g.n + 8.0 * c);
     const unsigned int nrec = hc[1];
     ctx->cur_block = mark_block;
     ctx->cur_off = mark_off;
@@ -498,6 +508,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
 int pcr_ransac_step_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, u64 seed,
                          long long h_begin, int count, double *T) {
     if (count <= 0) return PCR_OK;
+    KScope ks(ctx, KC_RANSAC_STEP, 120.0 * (double)count);
     k_ransac_step<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, seed, h_begin, count, T);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());
@@ -507,6 +518,7 @@ int pcr_ransac_step_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, con
 int pcr_inlier_count_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, const double *T,
                           int count, double thresh, int squared, int *counts) {
     if (count <= 0) return PCR_OK;
+    KScope ks(ctx, KC_RANSAC_STEP, 40.0 * (double)c * count);
     k_inlier_count<<<count, 256, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, T, thresh, squared, counts);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());

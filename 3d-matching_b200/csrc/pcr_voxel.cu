@@ -92,6 +92,7 @@ int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 
     PCR_ALLOC(cell, uint32_t, (size_t)n);
     PCR_ALLOC(packed, u64, (size_t)ncells + 1);
     PCR_ALLOC(sums, long long, 3 * (size_t)n);
+    KScope *ks = new KScope(ctx, KC_VOXEL, 40.0 * n + 24.0 * (double)ncells + 16.0 * n);
     PCR_CUDA(cudaMemsetAsync(packed, 0, sizeof(u64) * ((size_t)ncells + 1), ctx->stream));
     k_vox_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, g, cell, packed);
     PCR_LAUNCHED();
@@ -104,6 +105,7 @@ int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 
     const int blocks = (int)min((long long)div_up(ncells, 256), (long long)ctx->sm_count * 16);
     k_vox_finalize<<<blocks, 256, 0, ctx->stream>>>(packed, ncells, sums, ldexp(1.0, -k), out);
     PCR_LAUNCHED();
+    delete ks;
     PCR_CUDA(cudaGetLastError());
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     *m_host = (int)(*h_total >> 32);

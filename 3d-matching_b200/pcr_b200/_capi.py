@@ -50,6 +50,11 @@ class HypRecord(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    """pcr_kernel_stat"""
+    _fields_ = [("total_ms", C.c_double), ("launches", C.c_int64), ("bytes", C.c_double), ("flops", C.c_double)]
+
+
 class AlignParams(C.Structure):
     """pcr_align_params"""
     _fields_ = [
@@ -81,6 +86,7 @@ class AlignResult(C.Structure):
 # every symbol include/pcr.h declares (tests/test_capi_exports.py checks the list against the header)
 EXPORTS = [
     "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_set_stream", "pcr_version", "pcr_launch_count",
+    "pcr_set_profiling", "pcr_kernel_class_count", "pcr_kernel_class_name", "pcr_kernel_stats",
     "pcr_pack_xyz_f32", "pcr_pack_xyz_f64", "pcr_unpack_xyz_f32", "pcr_transform_points",
     "pcr_voxel_downsample", "pcr_estimate_normals", "pcr_compute_fpfh", "pcr_knn_hybrid", "pcr_nn1",
     "pcr_match_features", "pcr_nn_features",
@@ -109,6 +115,7 @@ def load():
         raise ImportError(f"{LIB_PATH} does not export {missing}: rebuild it (make -C 3d-matching_b200/csrc)")
     lib.pcr_last_error.restype = C.c_char_p
     lib.pcr_launch_count.restype = C.c_int64
+    lib.pcr_kernel_class_name.restype = C.c_char_p
     lib.pcr_align_default_params.restype = None
     _lib = lib
     return lib

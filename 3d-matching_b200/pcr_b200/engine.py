@@ -81,6 +81,20 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.pcr_launch_count(self.ctx))
 
+    def set_profiling(self, enabled: bool) -> None:
+        self.lib.pcr_set_profiling(self.ctx, C.c_int(int(enabled)))
+
+    def kernel_stats(self, reset: bool = True) -> dict:
+        """{class name: {ms, launches, bytes, flops}} accumulated since the last reset (synchronises the stream)."""
+        n = int(self.lib.pcr_kernel_class_count())
+        arr = (_capi.KernelStat * n)()
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_kernel_stats(self.ctx, arr, C.c_int(n), C.c_int(int(reset))))
+        return {self.lib.pcr_kernel_class_name(i).decode(): {"ms": arr[i].total_ms, "launches": arr[i].launches,
+                                                              "bytes": arr[i].bytes, "flops": arr[i].flops}
+                for i in range(n) if arr[i].launches}
+
     def pack(self, xyz) -> torch.Tensor:
         """(n,3) or (n,4) fp32/fp64 numpy / torch (host or device) -> (n,4) fp32 CUDA tensor (quantised, D1)."""
         if isinstance(xyz, torch.Tensor):

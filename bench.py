@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the registration hot path (contract in the task statement, §④).
+
+    python bench.py --gpus N --steps K --warmup W          # this engine
+    python bench.py --impl reference --steps K --warmup W  # the reference arm: the CPU oracle on the host cores
+
+Metric (BASELINE.json): end-to-end align ms @100k points.  One step = one full alignment of the config-2 pair
+(N_s = N_t = 100k synthetic points, voxel 0.005): voxel down-sampling, normals, FPFH, mutual feature matching,
+RANSAC over 100k hypotheses, full-resolution normals, 50 point-to-plane ICP iterations.  FIXED WORK: RANSAC
+confidence 1.0 (every hypothesis is scored, no early exit) and ICP relative criteria 0 (all 50 iterations run), so no
+work is skipped inside the timed region; the reference's default criteria (confidence 0.999, 30 iterations, 1e-6)
+are timed as well and reported under "aux".  At N > 1 every rank aligns its own pair (weak scaling, no data-path
+collective); value = max-over-ranks step time / N = ms per aligned pair for the whole job.
+
+`value`  : inputs already resident in HBM (pcr_align), CUDA events on the launching stream.
+`e2e`    : the same step through the public API with pinned HOST buffers (pcr_align_host): H2D copies of both
+           clouds and the D2H read of the result are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "3d-matching_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_POINTS = 100000
+VOXEL = 0.005
+RANSAC_ITERS = 100000
+ICP_ITERS = 50
+SEED_PAIR = 20242
+WORKLOAD = "cfg2: 100k-point pair, voxel 0.005, RANSAC 100k hypotheses (confidence 1.0, fixed work) + 50 ICP iterations (fixed)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops"),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pair(seed=SEED_PAIR, n=N_POINTS):
+    from pcr_b200 import synth
+    return synth.make_pair(n, VOXEL, seed)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (the reference's own arithmetic lives in the absent open3d wheel)
+# --------------------------------------------------------------------------------------------------------------------
+def oracle_step(orc, src, tgt, fixed=True):
+    S = orc.preprocess(src, VOXEL)
+    G = orc.preprocess(tgt, VOXEL)
+    conf = 1.0 if fixed else 0.999
+    r = orc.global_registration(S, G, VOXEL, RANSAC_ITERS, conf, 7)
+    if fixed:
+        i = orc.refine_registration(S, G, r.transformation, VOXEL, ICP_ITERS, 0.0, 0.0)
+    else:
+        i = orc.refine_registration(S, G, r.transformation, VOXEL)
+    return r, i
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 runs the CPU arm
+    from oracle import pcr_oracle as orc
+    orc.build()
+    cores = orc.num_threads()
+    src, tgt, _ = make_pair()
+    for _ in range(args.warmup):
+        oracle_step(orc, src, tgt)
+    t = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        r, i = oracle_step(orc, src, tgt)
+        t.append((time.perf_counter() - t0) * 1e3)
+    ms = float(np.mean(t))
+    line = {
+        "impl": "reference", "metric": "end-to-end align ms @100k pts", "value": ms, "unit": "ms", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU oracle (C/OpenMP restatement of the Open3D 0.19.0 semantics; open3d itself "
+                   "is absent and cannot be installed), all host threads, whole workload per step"},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": f"{args.steps} full alignments of the 100k pair"},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "result": {"fitness": i.fitness, "inlier_rmse": i.inlier_rmse, "ransac_best_hyp": r.best_hyp},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# this engine
+# --------------------------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pcr_b200.engine import get_engine
+    eng = get_engine(local)
+    peaks = load_peaks()
+
+    src, tgt, T_true = make_pair(SEED_PAIR + rank)
+    ds, dt = eng.pack(src), eng.pack(tgt)
+    src_pin = torch.from_numpy(src).pin_memory().numpy()
+    tgt_pin = torch.from_numpy(tgt).pin_memory().numpy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.tdev)  # > 126 MB L2
+
+    def params(fixed=True):
+        p = eng.default_params(VOXEL)
+        p.ransac_max_iter = RANSAC_ITERS
+        p.ransac_confidence = 1.0 if fixed else 0.999
+        p.seed = 7
+        p.icp_max_iter = ICP_ITERS if fixed else 30
+        p.icp_rel_fitness = 0.0 if fixed else 1e-6
+        p.icp_rel_rmse = 0.0 if fixed else 1e-6
+        p.source_normals = 1
+        return p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        res = None
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            res = fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        barrier()
+        ms = tot / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res
+
+    p_fixed, p_default = params(True), params(False)
+
+    # ---- device-resident arm (value) with per-kernel timing for the roofline --------------------------------------
+    eng.set_profiling(True)
+    eng.kernel_stats(reset=True)
+    clocks = ClockSampler(local)
+    l0 = eng.launch_count()
+    # warm-up outside the sampler
+    for _ in range(args.warmup):
+        eng.align_device(ds, dt, p_fixed)
+    eng.kernel_stats(reset=True)
+    l0 = eng.launch_count()
+    clocks.start()
+    ms_dev, res = timed(lambda: eng.align_device(ds, dt, p_fixed), args.steps, 0)
+    clk = clocks.stop()
+    launches = eng.launch_count() - l0
+    kstats = eng.kernel_stats(reset=True)
+    eng.set_profiling(False)
+
+    # ---- end-to-end arm: pinned host buffers in, result on the host out ----------------------------------------------
+    ms_e2e, res_e = timed(lambda: eng.align_host(src_pin, tgt_pin, p_fixed), args.steps, args.warmup)
+    ms_dev_np, _ = timed(lambda: eng.align_device(ds, dt, p_fixed), args.steps, 1)       # without profiling events
+    ms_default, res_d = timed(lambda: eng.align_host(src_pin, tgt_pin, p_default), args.steps, 1)
+
+    # ---- roofline of the dominant kernel class -----------------------------------------------------------------------
+    dom = max(kstats.items(), key=lambda kv: kv[1]["ms"]) if kstats else None
+    roof = None
+    step_total = sum(v["ms"] for v in kstats.values()) or 1.0
+    if dom:
+        name, st = dom
+        per_launch_ms = st["ms"] / max(st["launches"], 1)
+        if name == "nn_features" and st["flops"] > 0:
+            ach = st["flops"] / (st["ms"] * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
+        else:
+            ach = st["bytes"] / (st["ms"] * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None}
+        roof.update({"avg_launch_us": per_launch_ms * 1e3, "launches_per_step": st["launches"] / args.steps,
+                     "share_of_step": st["ms"] / step_total, "peak_source": peaks["source"],
+                     "algorithmic_bytes_per_launch": st["bytes"] / max(st["launches"], 1)})
+    # the ICP pass kernel is the kernel the north star sets a bandwidth target for: always report it too
+    icp = kstats.get("icp_pass")
+    icp_roof = None
+    if icp and icp["launches"]:
+        ach = icp["bytes"] / (icp["ms"] * 1e-3) / 1e9
+        icp_roof = {"achieved_gbs": ach, "frac": ach / peaks["hbm_gbs"], "avg_launch_us": icp["ms"] * 1e3 / icp["launches"],
+                    "bytes_per_launch": icp["bytes"] / icp["launches"]}
+
+    # ---- CPU baseline on rank 0 (bounded sample: full workload, few repetitions) ----------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import pcr_oracle as orc
+        orc.build()
+        reps = 2
+        oracle_step(orc, src, tgt)  # warm-up (page-in, thread pool)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ro, io = oracle_step(orc, src, tgt)
+        cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+        icp_c = res_e.icp
+        same = (np.array_equal(np.array(icp_c.transformation).reshape(4, 4), io.transformation)
+                and res_e.ransac.best_hyp == ro.best_hyp and icp_c.inlier_count == io.inlier_count)
+        cpu = {"value": cpu_ms, "unit": "ms", "cores": orc.num_threads(), "kind": "port",
+               "sample": f"{reps} full alignments of the same 100k pair (CPU oracle, OpenMP, all host threads)",
+               "results_identical_to_gpu": bool(same)}
+
+    # ---- aux: RANSAC hypotheses/s (sharded over ranks) and ICP iterations/s at 1M points -------------------------------
+    aux = {"align_ms_reference_default_criteria_e2e": ms_default,
+           "align_ms_device_resident_no_profiling_events": ms_dev_np,
+           "stage_ms_device": {k: float(v) for k, v in zip(
+               ["voxel", "normals_down", "fpfh", "match", "ransac", "normals_full", "icp", "total"], res.stage_ms)},
+           "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
+           "icp_pass_roofline_100k": icp_roof}
+    if not args.no_aux:
+        aux.update(run_aux(eng, args, world, rank, peaks))
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        icp_r = res_e.icp
+        line = {
+            "metric": "end-to-end align ms @100k pts", "value": ms_dev / world, "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 points / f64 solves / int64 fixed-point sums", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_src": N_POINTS, "n_tgt": N_POINTS, "voxel": VOXEL,
+                       "n_src_down": res.n_src_down, "n_tgt_down": res.n_tgt_down, "n_corr": res.n_corr,
+                       "parallelism": f"pair-parallel x{world} (one pair per GPU, no collective on the data path)",
+                       "l2": "256 MiB fill between timed steps (outside the per-step CUDA-event pair)",
+                       "source_full_res_normals": "computed (as Ply.__init__ does), although point-to-plane ICP never reads them"},
+            "e2e": {"value": ms_e2e / world, "unit": "ms", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(src.nbytes + tgt.nbytes), "d2h_bytes_per_step": int(ctypes_sizeof_result())},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "result": {"fitness": icp_r.fitness, "inlier_rmse": icp_r.inlier_rmse, "icp_iterations": icp_r.iterations,
+                       "ransac_hyp_evaluated": res_e.ransac.hyp_evaluated, "ransac_survivors": res_e.ransac.survivors,
+                       "max_abs_T_err_vs_truth": float(np.abs(np.array(icp_r.transformation).reshape(4, 4) - T_true).max())},
+            "aux": aux,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctypes_sizeof_result():
+    import ctypes
+    from pcr_b200 import _capi
+    return ctypes.sizeof(_capi.AlignResult)
+
+
+def run_aux(eng, args, world, rank, peaks):
+    """RANSAC hypotheses/s over all ranks (config 4 style, confidence 1.0) and ICP iterations/s at 1M points (config 3)."""
+    import torch
+    import torch.distributed as dist
+    from pcr_b200 import synth
+    from pcr_b200.dist import ransac_multi_gpu
+    out = {}
+    v = VOXEL
+    src, tgt, _ = make_pair(SEED_PAIR)  # every rank holds the SAME clouds for the sharded RANSAC
+    ds, dt = eng.pack(src), eng.pack(tgt)
+    sd, td = eng.voxel_downsample(ds, v).contiguous(), eng.voxel_downsample(dt, v).contiguous()
+    sn, tn = eng.estimate_normals(sd, 2 * v, 30), eng.estimate_normals(td, 2 * v, 30)
+    sf, tf = eng.compute_fpfh(sd, sn, 5 * v, 100), eng.compute_fpfh(td, tn, 5 * v, 100)
+    corr = eng.match_features(sf, tf, True).contiguous()
+    H = args.ransac_hyps
+    ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, 200000, 1.0, 7)  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r, st = ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, H, 1.0, 7)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out["ransac"] = {"hypotheses": H, "ms": ms, "hyp_per_s": H / (ms * 1e-3), "survivors": r.survivors,
+                     "checker_pass_rate": r.survivors / H, "best_hyp": r.best_hyp, "inlier_count": r.inlier_count,
+                     "waves": st["waves"], "n_gpus": world}
+    # ICP at 1M points: replicas only (single-pair ICP does not shard); aggregate = world x per-GPU rate
+    n = args.icp_points
+    s1, t1, _ = synth.make_icp_pair(n, v, 20243)
+    d1s, d1t = eng.pack(s1), eng.pack(t1)
+    nrm = eng.estimate_normals(d1t, 2 * v, 30)
+    for _ in range(2):  # warm-up: arena growth + consolidation happen here, not in the timed call
+        eng.icp_point_to_plane(d1s, d1t, nrm, 0.4 * v, np.eye(4), 5, 0.0, 0.0, want_corr=True)
+    eng.set_profiling(True)
+    eng.kernel_stats(reset=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g, _ = eng.icp_point_to_plane(d1s, d1t, nrm, 0.4 * v, np.eye(4), ICP_ITERS, 0.0, 0.0, want_corr=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    ks = eng.kernel_stats(reset=True).get("icp_pass")
+    eng.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    passes = g.iterations + 1
+    icp = {"points": n, "passes": passes, "call_ms": ms, "iters_per_s_whole_job": world * passes / (ms * 1e-3),
+           "fitness": g.fitness, "n_gpus": world, "parallelism": "replicas only"}
+    if ks and ks["launches"]:
+        us = ks["ms"] * 1e3 / ks["launches"]
+        gbs = ks["bytes"] / (ks["ms"] * 1e-3) / 1e9
+        icp.update({"pass_kernel_us": us, "pass_kernel_gbs_algorithmic_52B_per_point": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
+                    "kernel_iters_per_s_per_gpu": 1e6 / us})
+    out["icp_1m"] = icp
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-aux", action="store_true", help="skip the RANSAC hyp/s and 1M-point ICP legs")
+    ap.add_argument("--ransac-hyps", type=int, default=2000000)
+    ap.add_argument("--icp-points", type=int, default=1000000)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

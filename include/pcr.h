@@ -82,6 +82,20 @@ PCR_API int pcr_version(void);
 /* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
 PCR_API int64_t pcr_launch_count(pcr_ctx *ctx);
 
+/* Optional per-kernel timing (the CUDA-event twin of the reference's src/utils/profiler.py): when enabled,
+ * every kernel class is bracketed by an event pair on the context's stream.  pcr_kernel_stats synchronises the
+ * stream and returns, per class, accumulated device ms, launches and ALGORITHMIC bytes / flops. */
+typedef struct pcr_kernel_stat {
+    double total_ms;
+    int64_t launches;
+    double bytes;
+    double flops;
+} pcr_kernel_stat;
+PCR_API int pcr_set_profiling(pcr_ctx *ctx, int enabled);
+PCR_API int pcr_kernel_class_count(void);
+PCR_API const char *pcr_kernel_class_name(int id);
+PCR_API int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset);
+
 /* ---- layout helpers ------------------------------------------------------------------------------- */
 /* (n,3) fp32 or fp64 device array -> packed float4 cloud (quantisation to fp32, rule D1) */
 PCR_API int pcr_pack_xyz_f32(pcr_ctx *ctx, const float *xyz_dev, int n, float *xyzw_dev);
