@@ -152,28 +152,45 @@ __device__ __forceinline__ int grid_cell(double v, double o, double inv_h, int n
 // radius-limited 1-NN in a grid: best (d2, idx) under the (d2, idx) lexicographic order, d2 < r2 strictly.
 // Returns original index or -1.
 __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
-    const int cx = grid_cell((double)qx, g.ox, g.inv_h, g.nx);
-    const int cy = grid_cell((double)qy, g.oy, g.inv_h, g.ny);
-    const int cz = grid_cell((double)qz, g.oz, g.inv_h, g.nz);
+    const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
+    const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
+    const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
+    const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
     float best = r2;
     int bidx = -1;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     if (x0 <= x1) {
         const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
         const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-        for (int z = z0; z <= z1; z++) {
-            for (int y = y0; y <= y1; y++) {
-                const long long row = ((long long)z * g.ny + y) * g.nx;
-                const uint32_t b = __ldg(g.start + row + x0);
-                const uint32_t e = __ldg(g.start + row + x1 + 1);
-                for (uint32_t k = b; k < e; k++) {
-                    const float4 p = __ldg(g.sorted + k);
-                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    const int idx = __float_as_int(p.w);
-                    if (d2 < best || (d2 == best && bidx >= 0 && idx < bidx)) {
-                        best = d2;
-                        bidx = idx;
-                    }
+        // Rows are visited home row first; a row whose slab is provably farther than the best distance found so
+        // far is skipped.  The bound is conservative: slab distances (in cells) are shrunk by 1e-4 before
+        // squaring, which dominates the fp32 rounding of the few operations involved; rows at exactly the best
+        // distance are still visited (ties are decided by index).
+        const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
+        const float h2 = (float)(g.h * g.h);
+#pragma unroll 1
+        for (int o = 0; o < 9; o++) {
+            // o = 0 is the home row, then the 8 others
+            const int dy = (o == 0) ? 0 : ((o - 1) < 3 ? -1 : ((o - 1) < 5 ? 0 : 1));
+            const int dz = (o == 0) ? 0 : ((o - 1) < 3 ? (o - 2) : ((o - 1) < 5 ? ((o - 1) == 3 ? -1 : 1) : (o - 7)));
+            const int y = cy + dy, z = cz + dz;
+            if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+            if (o > 0) {
+                const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
+                const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
+                const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
+                if ((sy * sy + sz * sz) * h2 > best) continue;
+            }
+            const long long row = ((long long)z * g.ny + y) * g.nx;
+            const uint32_t b = __ldg(g.start + row + x0);
+            const uint32_t e = __ldg(g.start + row + x1 + 1);
+            for (uint32_t k = b; k < e; k++) {
+                const float4 p = __ldg(g.sorted + k);
+                const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                const int idx = __float_as_int(p.w);
+                if (d2 < best || (d2 == best && bidx >= 0 && idx < bidx)) {
+                    best = d2;
+                    bidx = idx;
                 }
             }
         }

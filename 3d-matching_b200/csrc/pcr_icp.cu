@@ -135,9 +135,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const float4 *__restri
     if (threadIdx.x < 12) sT[threadIdx.x] = S->T[threadIdx.x];
     const double scJJ = S->sc_JJ, scJr = S->sc_Jr, scd = S->sc_d;
     __syncthreads();
-    double T[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) T[i] = sT[i];
+    const double *T = sT;  // broadcast shared-memory reads keep 24 registers free for the accumulators
 
     long long acc[29];
 #pragma unroll

@@ -350,33 +350,42 @@ __global__ void __launch_bounds__(128) k_spfh(const float4 *__restrict__ pts, co
     }
 }
 
+// One warp per point.  FPFH[j] = (sum_k SPFH[nb_k][j] / d2_k) * (100 / S_b) + SPFH[i][j]  with the block normaliser
+// S_b accumulated in the reference's order (neighbour-major, bin-minor).  The quotients are produced once by all
+// lanes into a shared-memory chunk; the order-sensitive fp64 additions then read them back sequentially.
+constexpr int FPFH_CHUNK = 16;
 __global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx, const float *__restrict__ d2,
                                               const int *__restrict__ cnt, int max_nn,
                                               const double *__restrict__ spfh, float *__restrict__ out) {
+    __shared__ double sval[4][FPFH_CHUNK][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*val)[33] = sval[warp];
     for (int i = blockIdx.x * 4 + warp; i < n; i += gridDim.x * 4) {
         const int c = cnt[i];
-        double F0 = 0.0, F1 = 0.0;  // bins lane and (lane 0 only) 32
+        double F0 = 0.0, F1 = 0.0;  // bins `lane` and (lane 0 only) 32
         double sum = 0.0;           // lanes 0..2: normaliser of block `lane`
-        if (c > 1) {
-            for (int k = 1; k < c; k++) {
-                const double dist = (double)d2[(size_t)i * max_nn + k];
-                if (dist == 0.0) continue;
-                const double *hs = spfh + (size_t)idx[(size_t)i * max_nn + k] * 33;
-                F0 = F0 + hs[lane] / dist;
-                if (lane == 0) F1 = F1 + hs[32] / dist;
+        for (int k0 = 1; k0 < c; k0 += FPFH_CHUNK) {
+            const int nk = min(FPFH_CHUNK, c - k0);
+            for (int e = lane; e < nk * 33; e += 32) {
+                const int kk = e / 33, j = e - kk * 33;
+                const double dist = (double)d2[(size_t)i * max_nn + k0 + kk];
+                // a zero distance (duplicate point) is skipped by the reference; adding +0.0 is the same bits
+                val[kk][j] = dist == 0.0 ? 0.0 : spfh[(size_t)idx[(size_t)i * max_nn + k0 + kk] * 33 + j] / dist;
+            }
+            __syncwarp();
+            for (int kk = 0; kk < nk; kk++) {
+                F0 = F0 + val[kk][lane];
+                if (lane == 0) F1 = F1 + val[kk][32];
             }
             if (lane < 3) {
-                for (int k = 1; k < c; k++) {
-                    const double dist = (double)d2[(size_t)i * max_nn + k];
-                    if (dist == 0.0) continue;
-                    const double *hs = spfh + (size_t)idx[(size_t)i * max_nn + k] * 33 + 11 * lane;
+                for (int kk = 0; kk < nk; kk++) {
 #pragma unroll
-                    for (int j = 0; j < 11; j++) sum = sum + hs[j] / dist;
+                    for (int j = 0; j < 11; j++) sum = sum + val[kk][11 * lane + j];
                 }
-                if (sum != 0.0) sum = 100.0 / sum;
             }
+            __syncwarp();
         }
+        if (lane < 3 && sum != 0.0) sum = 100.0 / sum;
         const double s0 = __shfl_sync(0xffffffffu, sum, 0);
         const double s1 = __shfl_sync(0xffffffffu, sum, 1);
         const double s2 = __shfl_sync(0xffffffffu, sum, 2);

@@ -65,8 +65,22 @@ __global__ void __launch_bounds__(256) k_corr_all(const int *__restrict__ nn_s, 
     corr[2 * (size_t)i + 1] = nn_s[i];
 }
 
+int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn);
+
+// PCR_MATCH_EXACT=1 forces the CUDA-core exact kernel for every size (bring-up / A-B comparison aid)
+static bool match_use_tensor_cores() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PCR_MATCH_EXACT");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn) {
     if (nq == 0) return PCR_OK;
+    // tensor-core filter + exact certificate (pcr_match_tc.cu) once the problem fills at least a few tiles
+    if (nb >= 512 && nq >= 128 && match_use_tensor_cores()) return pcr_nn_features_tc_impl(ctx, fq, nq, fb, nb, nn);
     if (nb == 0) {
         PCR_CUDA(cudaMemsetAsync(nn, 0xff, sizeof(int) * (size_t)nq, ctx->stream));
         return PCR_OK;

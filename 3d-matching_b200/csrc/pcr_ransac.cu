@@ -237,16 +237,53 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
 #pragma unroll
         for (int i = 0; i < 12; i++) T[i] = sT[i];
         long long cnt = 0, sumq = 0, cin = 0;
-        for (int i = threadIdx.x; i < ms; i += VAL_THREADS) {
-            const float4 p = __ldg(src + i);
-            const float3 q = xform_pt(T, p.x, p.y, p.z);
-            float d2;
-            const int j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
-            if (j >= 0) {
-                cnt++;
-                sumq += fixed_ll((double)d2, sc_d);
+        // Exact pruning against the running best at wave start (a lower bound of the best the sequential loop
+        // holds when it reaches this hypothesis): stop as soon as the survivor can no longer be an improvement —
+        // its count cannot reach the best count, or it can at most tie the count while its sum of squared
+        // distances (which only grows) already reaches the best sum.  found/partial sums are block-uniform.
+        int found = 0;
+        long long partial = 0;
+        bool pruned = false;
+        for (int base = 0; base < ms; base += VAL_THREADS) {
+            const int i = base + threadIdx.x;
+            bool hit = false;
+            long long q_add = 0;
+            if (i < ms) {
+                const float4 p = __ldg(src + i);
+                const float3 q = xform_pt(T, p.x, p.y, p.z);
+                float d2;
+                const int j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+                if (j >= 0) {
+                    hit = true;
+                    cnt++;
+                    q_add = fixed_ll((double)d2, sc_d);
+                    sumq += q_add;
+                }
             }
+            found += __syncthreads_count(hit);
+            const int remaining = ms - min(ms, base + VAL_THREADS);
+            if ((long long)found + remaining < best_cnt) {
+                pruned = true;
+                break;
+            }
+            if (best_cnt > 0 && (long long)found + remaining == best_cnt) {
+                // only a tie on count is still possible: compare the partial sum (block-wide) with the best sum
+                const long long w = warp_sum_ll(q_add);
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][0] = w;
+                __syncthreads();
+                long long tot = 0;
+#pragma unroll
+                for (int k = 0; k < VAL_THREADS / 32; k++) tot += red[k][0];
+                partial += tot;
+                __syncthreads();
+                if (partial >= best_sumq) {
+                    pruned = true;
+                    break;
+                }
+            }  // chunks scored before the tie regime began are not in `partial`: it is a lower bound, which keeps
+               // the test conservative
         }
+        if (pruned) continue;  // block-uniform
         for (int i = threadIdx.x; i < c; i += VAL_THREADS) {
             const int2 cc = __ldg(corr + i);
             const float4 p = __ldg(src_orig + cc.x), q = __ldg(tgt + cc.y);
