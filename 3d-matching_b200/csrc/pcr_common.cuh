@@ -119,6 +119,9 @@ int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3])
 // build a search grid supporting radius-`radius` queries with a 3x3x3 cell probe.
 // If bounds are already known pass them (have_bounds), else they are computed.
 int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo, const float *hi, Grid *g);
+// Morton-order copy of a cloud (dense counting sort on interleaved cell ids; .w = original index): consecutive
+// points are spatially compact, which the warp-cooperative joins rely on
+int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out);
 // exclusive scan helpers (in pcr_grid.cu)
 int pcr_exclusive_scan_u32(pcr_ctx *ctx, uint32_t *data, long long n);  // in place, data[n] must exist (total)
 int pcr_exclusive_scan_u64(pcr_ctx *ctx, unsigned long long *data, long long n);
@@ -150,24 +153,34 @@ __device__ __forceinline__ int grid_cell(double v, double o, double inv_h, int n
 }
 
 // radius-limited 1-NN in a grid: best (d2, idx) under the (d2, idx) lexicographic order, d2 < r2 strictly.
-// Returns original index or -1.
-__device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
+// Returns original index or -1.  `seed` (optional, an index into `tgt_orig`, e.g. the previous ICP pass's
+// correspondence) only tightens the initial bound: the result is identical with or without it, because every
+// cell that intersects the closed ball of the current best distance is still visited (rows by slab distance,
+// cells of a row by x distance; both bounds carry a 1e-4-cell slack that dominates the fp32 rounding involved,
+// and cells at exactly the best distance are kept since ties are decided by index).
+__device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy, float qz, float r2, int seed,
+                                               const float4 *__restrict__ tgt_orig, float *d2_out) {
     const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
     const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
     const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
     const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
     float best = r2;
     int bidx = -1;
+    if (seed >= 0) {
+        const float4 p = __ldg(tgt_orig + seed);
+        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 < r2) {
+            best = d2;
+            bidx = seed;
+        }
+    }
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     if (x0 <= x1) {
         const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
         const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-        // Rows are visited home row first; a row whose slab is provably farther than the best distance found so
-        // far is skipped.  The bound is conservative: slab distances (in cells) are shrunk by 1e-4 before
-        // squaring, which dominates the fp32 rounding of the few operations involved; rows at exactly the best
-        // distance are still visited (ties are decided by index).
+        const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
         const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
-        const float h2 = (float)(g.h * g.h);
+        const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
 #pragma unroll 1
         for (int o = 0; o < 9; o++) {
             // o = 0 is the home row, then the 8 others
@@ -181,9 +194,13 @@ __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float
                 const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
                 if ((sy * sy + sz * sz) * h2 > best) continue;
             }
+            // cells of the row that can hold a point within the current best distance (in cell units, padded)
+            const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
+            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
+            if (xa > xb) continue;
             const long long row = ((long long)z * g.ny + y) * g.nx;
-            const uint32_t b = __ldg(g.start + row + x0);
-            const uint32_t e = __ldg(g.start + row + x1 + 1);
+            const uint32_t b = __ldg(g.start + row + xa);
+            const uint32_t e = __ldg(g.start + row + xb + 1);
             for (uint32_t k = b; k < e; k++) {
                 const float4 p = __ldg(g.sorted + k);
                 const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
@@ -197,6 +214,10 @@ __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float
     }
     *d2_out = best;
     return bidx;
+}
+
+__device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
+    return grid_nn1_seeded(g, qx, qy, qz, r2, -1, nullptr, d2_out);
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {

@@ -274,3 +274,60 @@ int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const 
     g->n = n;
     return PCR_OK;
 }
+
+// ---- Morton-order sort ---------------------------------------------------------------------------------------------
+struct MortonDims {
+    double ox, oy, oz, inv_c;
+    int lim;  // 2^L - 1
+};
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 8 bits -> every third bit
+    v &= 0xffu;
+    v = (v | (v << 8)) & 0x00f00fu;
+    v = (v | (v << 4)) & 0x0c30c3u;
+    v = (v | (v << 2)) & 0x249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton_count(const float4 *__restrict__ pts, int n, MortonDims g,
+                                                      uint32_t *__restrict__ cell, uint32_t *__restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pts + i);
+    const int cx = min(max((int)floor(((double)p.x - g.ox) * g.inv_c), 0), g.lim);
+    const int cy = min(max((int)floor(((double)p.y - g.oy) * g.inv_c), 0), g.lim);
+    const int cz = min(max((int)floor(((double)p.z - g.oz) * g.inv_c), 0), g.lim);
+    const uint32_t c = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+    cell[i] = c;
+    atomicAdd(count + c, 1u);
+}
+
+int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out) {
+    if (n <= 0) return pcr_fail(ctx, PCR_ERR_INVALID, "morton sort: empty cloud");
+    float lo[3], hi[3];
+    PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));
+    double ext = 0.0;
+    for (int d = 0; d < 3; d++) {
+        if (!(lo[d] <= hi[d]) || isinf(lo[d]) || isinf(hi[d])) return pcr_fail(ctx, PCR_ERR_INVALID, "morton sort: non-finite coordinates");
+        ext = fmax(ext, (double)hi[d] - (double)lo[d]);
+    }
+    int L = 4;
+    while (L < 8 && (1LL << (3 * L)) < 4LL * n) L++;
+    const long long ncells = 1LL << (3 * L);
+    MortonDims md{(double)lo[0], (double)lo[1], (double)lo[2], ext > 0.0 ? (double)(1 << L) / (ext * (1.0 + 1e-6)) : 0.0, (1 << L) - 1};
+    PCR_ALLOC(cell, uint32_t, (size_t)n);
+    PCR_ALLOC(start, uint32_t, (size_t)ncells + 1);
+    PCR_ALLOC(fill, uint32_t, (size_t)ncells);
+    PCR_ALLOC(sorted, float4, (size_t)n);
+    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 16.0 * (double)ncells);
+    PCR_CUDA(cudaMemsetAsync(start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), ctx->stream));
+    PCR_CUDA(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)ncells, ctx->stream));
+    k_morton_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, md, cell, start);
+    PCR_LAUNCHED();
+    PCR_TRY(pcr_exclusive_scan_u32(ctx, start, ncells));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, start, fill, sorted);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    *sorted_out = sorted;
+    return PCR_OK;
+}

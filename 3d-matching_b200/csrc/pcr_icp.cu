@@ -1,12 +1,15 @@
 // pcr_icp.cu — point-to-plane ICP (K9 + K10 + K11 fused), replaces open3d registration_icp as called from
 // src/matcher/icp.py:42-48.
 //
-// One kernel launch per NN pass: every source point is transformed by the cumulative fp64 transform (D7),
-// its radius-limited nearest target point is found in the uniform grid, and the point-to-plane normal
-// equations (21 + 6 sums), the inlier count and sum of squared distances are accumulated as int64 fixed
-// point (D5: order-free, so warp shuffles and atomics give bit-reproducible sums).  The last block to
-// finish solves the 6x6 system (LDL^T), composes the Euler-ZYX update, applies the convergence test and
-// publishes the next transform — the host launches max_iter+1 passes back to back with no synchronisation.
+// Two kernel launches per NN pass, no host synchronisation between passes:
+//   k_icp_nn    — every (Morton-ordered) source point is transformed by the cumulative fp64 transform (D7) and its
+//                 radius-limited nearest target point is found in the uniform grid.  The search is a chain of
+//                 dependent loads (cell range -> candidates), i.e. memory-latency bound, so this kernel is kept
+//                 lean (few registers, maximum occupancy) to keep many loads in flight.
+//   k_icp_accum — the point-to-plane normal equations (21 + 6 sums), the inlier count and the sum of squared
+//                 distances are accumulated as int64 fixed point (D5: order-free, so warp shuffles and atomics
+//                 give bit-reproducible sums); the last block to finish solves the 6x6 system (LDL^T), composes
+//                 the Euler-ZYX update, applies the convergence test and publishes the next transform.
 //
 // HBM roofline: 16 B source + 16 B target + 16 B normal + 4 B index = 52 B per point and pass.
 #include "pcr_common.cuh"
@@ -31,30 +34,44 @@ struct IcpState {
 
 __device__ int ldlt6_solve_dev(const double A[6][6], const double *b, double *x) {
     double L[6][6], d[6], y[6];
+    bool bad = false;
+#pragma unroll
     for (int i = 0; i < 6; i++)
+#pragma unroll
         for (int j = 0; j < 6; j++) L[i][j] = 0.0;
+#pragma unroll
     for (int j = 0; j < 6; j++) {
         double dj = A[j][j];
+#pragma unroll
         for (int k = 0; k < j; k++) dj = dj - (L[j][k] * L[j][k]) * d[k];
-        if (!(dj > 0.0) || isinf(dj)) return -1;
+        bad = bad || !(dj > 0.0) || isinf(dj);
         d[j] = dj;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
             double v = A[i][j];
+#pragma unroll
             for (int k = 0; k < j; k++) v = v - (L[i][k] * L[j][k]) * d[k];
             L[i][j] = v / dj;
         }
     }
+    if (bad) return -1;
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double v = b[i];
+#pragma unroll
         for (int k = 0; k < i; k++) v = v - L[i][k] * y[k];
         y[i] = v;
     }
+#pragma unroll
     for (int i = 0; i < 6; i++) y[i] = y[i] / d[i];
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
         double v = y[i];
+#pragma unroll
         for (int k = i + 1; k < 6; k++) v = v - L[k][i] * x[k];
         x[i] = v;
     }
+#pragma unroll
     for (int i = 0; i < 6; i++)
         if (isnan(x[i]) || isinf(x[i])) return -1;
     return 0;
@@ -124,10 +141,29 @@ __device__ void icp_finish_pass(IcpState *S, int ns) {
 
 constexpr int ICP_THREADS = 256;
 
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const float4 *__restrict__ src, int ns, Grid g,
-                                                          const float4 *__restrict__ tgt,
-                                                          const float4 *__restrict__ nrm, float r2,
-                                                          IcpState *__restrict__ S, int *__restrict__ corr) {
+// NN half of a pass.  seed[i] (Morton order) holds the previous pass's correspondence on entry (-1 in pass 0; it
+// only tightens the initial search bound) and this pass's on exit; d2s[i] the fp32 squared distance.
+__global__ void __launch_bounds__(256) k_icp_nn(const float4 *__restrict__ src, int ns, Grid g, const float4 *__restrict__ tgt,
+                                                float r2, const IcpState *__restrict__ S, int *__restrict__ seed,
+                                                float *__restrict__ d2s) {
+    if (S->done) return;
+    __shared__ double sT[12];
+    if (threadIdx.x < 12) sT[threadIdx.x] = S->T[threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(src + i);
+        const float3 q = xform_pt(sT, p.x, p.y, p.z);
+        float d2;
+        const int j = grid_nn1_seeded(g, q.x, q.y, q.z, r2, seed[i], tgt, &d2);
+        seed[i] = j;
+        d2s[i] = d2;
+    }
+}
+
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_accum(const float4 *__restrict__ src, int ns,
+                                                           const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
+                                                           IcpState *__restrict__ S, const int *__restrict__ seed,
+                                                           const float *__restrict__ d2s) {
     if (S->done) return;
     __shared__ double sT[12];
     __shared__ long long red[ICP_THREADS / 32][29];
@@ -142,12 +178,11 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const float4 *__restri
     for (int i = 0; i < 29; i++) acc[i] = 0;
 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(src + i);
-        const float3 q = xform_pt(T, p.x, p.y, p.z);
-        float d2;
-        const int j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
-        if (corr) corr[__float_as_int(p.w)] = j;
+        const int j = seed[i];
         if (j >= 0) {
+            const float4 p = __ldg(src + i);
+            const float3 q = xform_pt(T, p.x, p.y, p.z);
+            const float d2 = d2s[i];
             const float4 tp = __ldg(tgt + j);
             const float4 np = __ldg(nrm + j);
             const double sx = q.x, sy = q.y, sz = q.z;
@@ -197,6 +232,13 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(const float4 *__restri
         __threadfence();
         icp_finish_pass(S, ns);
     }
+}
+
+// correspondences from Morton order back to the caller's source order
+__global__ void __launch_bounds__(256) k_unpermute_corr(const float4 *__restrict__ src_sorted, const int *__restrict__ seed, int ns,
+                                                        int *__restrict__ corr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns) corr[__float_as_int(__ldg(src_sorted + i).w)] = seed[i];
 }
 
 __global__ void __launch_bounds__(256) k_nn1(const float4 *__restrict__ q, int nq, Grid g, float r2,
@@ -249,7 +291,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     Grid g;
     PCR_TRY(pcr_grid_build(ctx, tgt, nt, max_dist, lo, hi, &g));
     const float4 *src_sorted = nullptr;
-    PCR_TRY(pcr_sort_cloud_spatially(ctx, src, ns, max_dist * 4.0, &src_sorted));
+    PCR_TRY(pcr_morton_sort(ctx, src, ns, &src_sorted));
 
     const int lg = pcr_ilog2ceil(ns > 1 ? ns : 1);
     const int e_r = pcr_pow2ceil_exp(max_dist);
@@ -267,16 +309,26 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     hS->sc_Jr = ldexp(1.0, k_Jr); hS->isc_Jr = ldexp(1.0, -k_Jr);
     hS->sc_d = ldexp(1.0, k_d);   hS->isc_d = ldexp(1.0, -k_d);
     PCR_ALLOC(dS, IcpState, 1);
+    PCR_ALLOC(seed, int, (size_t)ns);
+    PCR_ALLOC(d2s, float, (size_t)ns);
+    PCR_CUDA(cudaMemsetAsync(seed, 0xff, sizeof(int) * (size_t)ns, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     const float r2 = (float)(max_dist * max_dist);
-    const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * 8);
+    const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * 4);
+    const int nn_blocks = min(div_up(ns, 256), ctx->sm_count * 8);
     const size_t pend_idx = ctx->pending.size();
     {
         KScope ks(ctx, KC_ICP_PASS, 16.0 * ns + 32.0 * nt + 4.0 * ns, max_iter + 1);
         for (int pass = 0; pass <= max_iter; pass++) {
-            k_icp_pass<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, g, tgt, nrm, r2, dS, corr);
+            k_icp_nn<<<nn_blocks, 256, 0, ctx->stream>>>(src_sorted, ns, g, tgt, r2, dS, seed, d2s);
+            PCR_LAUNCHED();
+            k_icp_accum<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, tgt, nrm, dS, seed, d2s);
             PCR_LAUNCHED();
         }
+    }
+    if (corr) {
+        k_unpermute_corr<<<div_up(ns, 256), 256, 0, ctx->stream>>>(src_sorted, seed, ns, corr);
+        PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
     PCR_CUDA(cudaMemcpyAsync(hS, dS, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));

@@ -96,6 +96,104 @@ __device__ __forceinline__ int warp_knn_hybrid(const Grid &g, float qx, float qy
     return cnt < max_nn ? cnt : max_nn;
 }
 
+// ---- register-resident variant for max_nn <= 32 ----------------------------------------------------------------------
+// The current best keys live one per lane, sorted ascending by lane.  A 32-wide scan step with many admissible
+// candidates is bitonic-sorted across the warp and merged (min(best[i], cand[31-i]) + bitonic merge); a step with
+// few candidates inserts them one by one (ballot-rank + shuffle-up).  Rows are visited home row first and a row
+// whose slab is provably farther than the current max_nn-th distance is skipped (same bound as grid_nn1).
+__device__ __forceinline__ u64 warp_bitonic_sort32(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            v = keep_min ? (o < v ? o : v) : (o > v ? o : v);
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ u64 warp_bitonic_merge32(u64 v, int lane) {  // v bitonic -> ascending
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
+        v = ((lane & j) == 0) ? (o < v ? o : v) : (o > v ? o : v);
+    }
+    return v;
+}
+
+// returns the number of neighbours (<= max_nn <= 32); *best_out = this lane's key of the ascending list
+__device__ __forceinline__ int warp_knn_top32(const Grid &g, float qx, float qy, float qz, float r2, int max_nn, int lane,
+                                              u64 *best_out) {
+    const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
+    const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
+    const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
+    const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
+    const u64 INF = ~0ull;
+    u64 best = INF;
+    u64 thr = ((u64)__float_as_uint(r2)) << 32;  // admissible: key < thr
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    if (x0 <= x1) {
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+        const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
+        const float h2 = (float)(g.h * g.h);
+#pragma unroll 1
+        for (int o = 0; o < 9; o++) {
+            const int dy = (o == 0) ? 0 : ((o - 1) < 3 ? -1 : ((o - 1) < 5 ? 0 : 1));
+            const int dz = (o == 0) ? 0 : ((o - 1) < 3 ? (o - 2) : ((o - 1) < 5 ? ((o - 1) == 3 ? -1 : 1) : (o - 7)));
+            const int y = cy + dy, z = cz + dz;
+            if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+            if (o > 0) {
+                const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
+                const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
+                const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
+                // skip only if strictly farther than the admission threshold's distance (ties are kept)
+                if ((sy * sy + sz * sz) * h2 > __uint_as_float((uint32_t)(thr >> 32))) continue;
+            }
+            const long long row = ((long long)z * g.ny + y) * g.nx;
+            const uint32_t b = __ldg(g.start + row + x0);
+            const uint32_t e = __ldg(g.start + row + x1 + 1);
+            for (uint32_t base = b; base < e; base += 32) {
+                const uint32_t k = base + lane;
+                u64 key = INF;
+                if (k < e) {
+                    const float4 p = __ldg(g.sorted + k);
+                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    key = (((u64)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, key < thr);
+                if (m == 0) continue;
+                if (__popc(m) > 3) {
+                    u64 c = key < thr ? key : INF;
+                    c = warp_bitonic_sort32(c, lane);
+                    const u64 rev = __shfl_sync(0xffffffffu, c, 31 - lane);
+                    best = warp_bitonic_merge32(rev < best ? rev : best, lane);
+                } else {
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u64 ck = __shfl_sync(0xffffffffu, key, src);
+                        if (!(ck < thr)) continue;  // the threshold may have tightened since the ballot
+                        const int pos = __popc(__ballot_sync(0xffffffffu, best < ck));
+                        const u64 up = __shfl_up_sync(0xffffffffu, best, 1);
+                        best = lane < pos ? best : (lane == pos ? ck : up);
+                        const u64 t = __shfl_sync(0xffffffffu, best, max_nn - 1);
+                        if (t < thr) thr = t;
+                    }
+                    continue;
+                }
+                const u64 t = __shfl_sync(0xffffffffu, best, max_nn - 1);
+                if (t < thr) thr = t;
+            }
+        }
+    }
+    *best_out = best;
+    const int found = __popc(__ballot_sync(0xffffffffu, best != INF));
+    return found < max_nn ? found : max_nn;
+}
+
 // ---- MODE_LIST: neighbour lists to global memory ------------------------------------------------------------
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_list(const float4 *__restrict__ queries, int nq, Grid g,
                                                              float r2, int max_nn, int *__restrict__ idx,
@@ -126,7 +224,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__rest
     u64 *buf = sbuf[warp];
     for (int q = blockIdx.x * KNN_WARPS + warp; q < n; q += gridDim.x * KNN_WARPS) {
         const float4 p = __ldg(pts + q);
-        const int c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
+        int c;
+        if (max_nn <= 32) {  // warp-uniform
+            u64 mine;
+            c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
+            buf[lane] = mine;
+            __syncwarp();
+        } else {
+            c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
+        }
         double cu = 0.0;
         if (c >= 3 && lane < 9) {
             for (int k = 0; k < c; k++) {

@@ -17,6 +17,7 @@
 //                   bound of every non-candidate (4th score - error bound); other rows go to the exact kernel.
 // The result is therefore bit-identical to k_nn_features_exact for every row.
 #include <cuda_bf16.h>
+#include <stdio.h>
 
 #include "pcr_common.cuh"
 
@@ -232,19 +233,33 @@ __global__ void __launch_bounds__(128, 1) k_match_tc(const __nv_bfloat16 *__rest
             for (int cch = 0; cch < TC_N / 32; cch++) {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cch * 32), v);
+                // scores of the 32 columns, then one min-tree: a chunk that cannot enter the top-4 costs ~2 instr/value
+                float sc[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float s = fmaf(-2.0f, __uint_as_float(v[j]), nb[cch * 32 + j]);
-                    if (s < s3) {
-                        const int col = t * TC_N + cch * 32 + j;
-                        if (s < s2) {
-                            s3 = s2; i3 = i2;
-                            if (s < s1) {
-                                s2 = s1; i2 = i1;
-                                if (s < s0) { s1 = s0; i1 = i0; s0 = s; i0 = col; }
-                                else { s1 = s; i1 = col; }
-                            } else { s2 = s; i2 = col; }
-                        } else { s3 = s; i3 = col; }
+                for (int j = 0; j < 32; j++) sc[j] = fmaf(-2.0f, __uint_as_float(v[j]), nb[cch * 32 + j]);
+                float m16[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) m16[j] = fminf(sc[j], sc[j + 16]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) m16[j] = fminf(m16[j], m16[j + 8]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) m16[j] = fminf(m16[j], m16[j + 4]);
+                const float cmin = fminf(fminf(m16[0], m16[1]), fminf(m16[2], m16[3]));
+                if (cmin < s3) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float s = sc[j];
+                        if (s < s3) {
+                            const int col = t * TC_N + cch * 32 + j;
+                            if (s < s2) {
+                                s3 = s2; i3 = i2;
+                                if (s < s1) {
+                                    s2 = s1; i2 = i1;
+                                    if (s < s0) { s1 = s0; i1 = i0; s0 = s; i0 = col; }
+                                    else { s1 = s; i1 = col; }
+                                } else { s2 = s; i2 = col; }
+                            } else { s3 = s; i3 = col; }
+                        }
                     }
                 }
             }
@@ -274,36 +289,46 @@ __device__ __forceinline__ double exact_dist(const float *__restrict__ a, const 
     return acc;
 }
 
+// one warp per query row: lane l re-scores candidate l (n_split * 4 <= 64 candidates, two rounds at most)
 __global__ void __launch_bounds__(128) k_match_recheck(const float *__restrict__ fq, int nq, const float *__restrict__ fb, int nb,
                                                        const int *__restrict__ cand_idx, const float *__restrict__ cand_kth,
                                                        int n_split, const unsigned int *__restrict__ max_nrm2_bits,
                                                        int *__restrict__ nn, int *__restrict__ fallback_rows,
                                                        unsigned int *__restrict__ n_fallback) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nq) return;
     float a[33];
     double na = 0.0;
 #pragma unroll
     for (int k = 0; k < 33; k++) {
-        a[k] = fq[(size_t)q * 33 + k];
+        a[k] = __ldg(fq + (size_t)q * 33 + k);
         na += (double)a[k] * (double)a[k];
     }
     double best = INFINITY;
-    int bi = -1;
+    int bi = 0x7fffffff;
     float kth = INFINITY;
-    for (int sp = 0; sp < n_split; sp++) {
-        kth = fminf(kth, cand_kth[(size_t)sp * nq + q]);
-        for (int c = 0; c < TC_NCAND; c++) {
-            const int j = cand_idx[((size_t)sp * nq + q) * TC_NCAND + c];
-            if (j < 0 || j >= nb) continue;
-            const double d = exact_dist(a, fb + (size_t)j * 33);
-            if (d < best || (d == best && j < bi)) { best = d; bi = j; }
-        }
+    const int ncand = n_split * TC_NCAND;
+    for (int c = lane; c < ncand; c += 32) {
+        const int sp = c / TC_NCAND, k = c - sp * TC_NCAND;
+        if (k == 0) kth = fminf(kth, cand_kth[(size_t)sp * nq + q]);
+        const int j = cand_idx[((size_t)sp * nq + q) * TC_NCAND + k];
+        if (j < 0 || j >= nb) continue;
+        const double d = exact_dist(a, fb + (size_t)j * 33);
+        if (d < best || (d == best && j < bi)) { best = d; bi = j; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const float ok = __shfl_xor_sync(0xffffffffu, kth, o);
+        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+        kth = fminf(kth, ok);
+    }
+    if (lane != 0) return;
     // every non-candidate j has score_j >= kth, and true ||a-b_j||^2 >= ||a||^2 + score_j - eps
     const double bmax = sqrt((double)__uint_as_float(*max_nrm2_bits));
     const double eps = 1.5e-4 * sqrt(na) * bmax + 1e-6 * (bmax * bmax + na) + 1e-30;
-    const bool ok = (bi >= 0) && (kth == INFINITY || best < (na + (double)kth) - eps);
+    const bool ok = (bi != 0x7fffffff) && (kth == INFINITY || best < (na + (double)kth) - eps);
     if (ok) {
         nn[q] = bi;
     } else {
@@ -312,24 +337,25 @@ __global__ void __launch_bounds__(128) k_match_recheck(const float *__restrict__
     }
 }
 
-// exact scan for the rows that failed the certificate (device-side count, no host sync)
-__global__ void __launch_bounds__(128) k_match_fallback(const float *__restrict__ fq, const float *__restrict__ fb, int nb,
-                                                        const int *__restrict__ rows, const unsigned int *__restrict__ n_rows,
-                                                        int *__restrict__ nn) {
+// exact scan for the rows that failed the certificate (device-side count, no host sync): one CTA per row
+constexpr int FB_THREADS = 256;
+__global__ void __launch_bounds__(FB_THREADS) k_match_fallback(const float *__restrict__ fq, const float *__restrict__ fb, int nb,
+                                                               const int *__restrict__ rows, const unsigned int *__restrict__ n_rows,
+                                                               int *__restrict__ nn) {
+    __shared__ double sd[FB_THREADS / 32];
+    __shared__ int si[FB_THREADS / 32];
     const unsigned int n = *n_rows;
-    // one warp per row: lanes stride over base rows, then a (d, idx) warp arg-min
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int r = warp_global; r < n; r += n_warps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned int r = blockIdx.x; r < n; r += gridDim.x) {
         const int q = rows[r];
         float a[33];
 #pragma unroll
-        for (int k = 0; k < 33; k++) a[k] = fq[(size_t)q * 33 + k];
+        for (int k = 0; k < 33; k++) a[k] = __ldg(fq + (size_t)q * 33 + k);
         double best = INFINITY;
         int bi = 0x7fffffff;
-        for (int j = lane; j < nb; j += 32) {
+        for (int j = threadIdx.x; j < nb; j += FB_THREADS) {
             const double d = exact_dist(a, fb + (size_t)j * 33);
-            if (d < best) { best = d; bi = j; }  // ascending j per lane: strict < keeps the lowest index
+            if (d < best) { best = d; bi = j; }  // ascending j per thread: strict < keeps the lowest index
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -337,7 +363,14 @@ __global__ void __launch_bounds__(128) k_match_fallback(const float *__restrict_
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
         }
-        if (lane == 0) nn[q] = bi;
+        __syncthreads();
+        if (lane == 0) { sd[warp] = best; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < FB_THREADS / 32; w++)
+                if (sd[w] < best || (sd[w] == best && si[w] < bi)) { best = sd[w]; bi = si[w]; }
+            nn[q] = bi;
+        }
     }
 }
 
@@ -401,12 +434,18 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
     }
     {
         KScope ks(ctx, KC_MATCH_MISC, 132.0 * nq * (1 + TC_NCAND * n_split), 2);
-        k_match_recheck<<<div_up(nq, 128), 128, 0, ctx->stream>>>(fq, nq, fb, nb, cand_idx, cand_kth, n_split, B.max_bits, nn, fb_rows,
+        k_match_recheck<<<div_up((long long)nq * 32, 128), 128, 0, ctx->stream>>>(fq, nq, fb, nb, cand_idx, cand_kth, n_split, B.max_bits, nn, fb_rows,
                                                                   n_fb);
         PCR_LAUNCHED();
-        k_match_fallback<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(fq, fb, nb, fb_rows, n_fb, nn);
+        k_match_fallback<<<ctx->sm_count * 4, FB_THREADS, 0, ctx->stream>>>(fq, fb, nb, fb_rows, n_fb, nn);
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
+    if (getenv("PCR_DEBUG")) {  // bring-up aid: how many rows needed the exact fallback
+        unsigned int h = 0;
+        cudaMemcpyAsync(&h, n_fb, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[pcr] match tc: nq=%d nb=%d n_split=%d fallback rows=%u\n", nq, nb, n_split, h);
+    }
     return PCR_OK;
 }

@@ -248,11 +248,12 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
             const int i = base + threadIdx.x;
             bool hit = false;
             long long q_add = 0;
-            if (i < ms) {
-                const float4 p = __ldg(src + i);
+            {
+                const bool valid = i < ms;
+                const float4 p = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float3 q = xform_pt(T, p.x, p.y, p.z);
                 float d2;
-                const int j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+                const int j = valid ? grid_nn1(g, q.x, q.y, q.z, r2, &d2) : -1;
                 if (j >= 0) {
                     hit = true;
                     cnt++;
@@ -397,9 +398,7 @@ int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tg
                        RansacWork *w) {
     PCR_TRY(pcr_grid_build(ctx, tgt, mt, max_dist, nullptr, nullptr, &w->g));
     // source in cell order of a grid over itself: lanes of a warp then probe neighbouring target cells
-    Grid gs;
-    PCR_TRY(pcr_grid_build(ctx, src, ms, max_dist * 2.0, nullptr, nullptr, &gs));
-    w->src_sorted = gs.sorted;
+    PCR_TRY(pcr_morton_sort(ctx, src, ms, &w->src_sorted));
     w->r2 = (float)(max_dist * max_dist);
     w->k_d = pcr_ransac_k_d(max_dist, ms);
     return PCR_OK;
