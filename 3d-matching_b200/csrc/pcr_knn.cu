@@ -165,7 +165,7 @@ __device__ __forceinline__ int warp_knn_top32(const Grid &g, float qx, float qy,
                 }
                 unsigned m = __ballot_sync(0xffffffffu, key < thr);
                 if (m == 0) continue;
-                if (__popc(m) > 3) {
+                if (__popc(m) > 12) {  // an insertion is ~8 dependent instructions, a sort + merge ~160
                     u64 c = key < thr ? key : INF;
                     c = warp_bitonic_sort32(c, lane);
                     const u64 rev = __shfl_sync(0xffffffffu, c, 31 - lane);
@@ -235,23 +235,17 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__rest
         }
         double cu = 0.0;
         if (c >= 3 && lane < 9) {
+            // lane l accumulates cumulant l = A*B with A, B in {1, x, y, z} chosen by value selects (no divergent
+            // switch); x*1.0 is exact, so lanes 0..2 still add the bare coordinate
+            const int ia = lane < 3 ? lane + 1 : (lane < 6 ? 1 : (lane < 8 ? 2 : 3));
+            const int ib = lane < 3 ? 0 : (lane < 6 ? lane - 2 : (lane < 8 ? lane - 4 : 3));
             for (int k = 0; k < c; k++) {
                 const int j = (int)(uint32_t)(buf[k] & 0xffffffffull);
                 const float4 pj = __ldg(pts + j);
                 const double x = pj.x, y = pj.y, z = pj.z;
-                double term;
-                switch (lane) {
-                    case 0: term = x; break;
-                    case 1: term = y; break;
-                    case 2: term = z; break;
-                    case 3: term = x * x; break;
-                    case 4: term = x * y; break;
-                    case 5: term = x * z; break;
-                    case 6: term = y * y; break;
-                    case 7: term = y * z; break;
-                    default: term = z * z; break;
-                }
-                cu = cu + term;
+                const double A = ia == 1 ? x : (ia == 2 ? y : z);
+                const double B = ib == 0 ? 1.0 : (ib == 1 ? x : (ib == 2 ? y : z));
+                cu = cu + A * B;
             }
             cu = cu / (double)c;
         }

@@ -31,6 +31,17 @@ for p in (ROOT, os.path.join(ROOT, "3d-matching_b200")):
 
 import numpy as np  # noqa: E402
 
+# keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+os.environ["NCCL_DEBUG"] = "WARN"
+
+
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
 N_POINTS = 100000
 VOXEL = 0.005
 RANSAC_ITERS = 100000
@@ -123,6 +134,7 @@ def run_reference(args):
         return  # under torchrun only rank 0 runs the CPU arm
     from oracle import pcr_oracle as orc
     orc.build()
+    orc.set_num_threads(host_threads())
     cores = orc.num_threads()
     src, tgt, _ = make_pair()
     for _ in range(args.warmup):
@@ -264,6 +276,7 @@ def run_engine(args):
     if rank == 0 and not args.no_cpu:
         from oracle import pcr_oracle as orc
         orc.build()
+        orc.set_num_threads(host_threads())
         reps = 2
         oracle_step(orc, src, tgt)  # warm-up (page-in, thread pool)
         t0 = time.perf_counter()

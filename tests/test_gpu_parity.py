@@ -259,3 +259,28 @@ def test_align_end_to_end(orc, eng, pair):
     assert np.array_equal(T, T2) and fit == fit2 and rmse == rmse2
     with pytest.raises(ValueError):
         align(np.zeros((0, 3)), pair["tgt"], v)
+
+
+def test_tensor_core_matching_is_exact(orc, eng):
+    """Sizes that take the tcgen05 path (pcr_match_tc.cu): the certificate + fallback must reproduce the exact
+    fp64 arg-min bit for bit, including exact ties, duplicated rows and all-zero descriptors."""
+    rng = np.random.default_rng(21)
+    for nq, nb in ((700, 1500), (1300, 2600)):
+        fs = rng.uniform(0, 200, (nq, 33)).astype(np.float32)
+        ft = rng.uniform(0, 200, (nb, 33)).astype(np.float32)
+        ft[100:140] = ft[50]            # 41 identical base rows: top-4 candidates cannot certify -> fallback
+        fs[7] = ft[50]                  # exact tie over those rows -> lowest index 50
+        fs[300:320] = 0.0
+        ft[600:700] = 0.0               # all-zero descriptors tie exactly
+        ft[900] = fs[11]
+        ft[901] = fs[11] + np.float32(1e-3)   # near-tie well inside the bf16 error bound
+        # smooth, highly correlated descriptors (what real FPFH looks like): small nearest-neighbour gaps
+        base = rng.uniform(0, 200, 33).astype(np.float32)
+        fs[400:600] = base + rng.normal(0, 0.05, (200, 33)).astype(np.float32)
+        ft[1000:1400] = base + rng.normal(0, 0.05, (400, 33)).astype(np.float32)
+        dfs, dft = torch.from_numpy(fs).cuda(), torch.from_numpy(ft).cuda()
+        nn = eng.nn_features(dfs, dft).cpu().numpy()
+        ref = orc.nn_features(fs, ft)
+        assert np.array_equal(nn, ref)
+        assert nn[7] == 50 and nn[300] == 600
+        assert np.array_equal(eng.match_features(dfs, dft, True, 0.0).cpu().numpy(), orc.match_features(fs, ft, True, 0.0))
