@@ -50,6 +50,9 @@ struct pcr_ctx {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     bool busy = false;
+    // bounding boxes already reduced during the current exported call, keyed by (pointer, n); cleared on entry
+    struct BoundsEntry { const void *ptr; int n; float lo[3], hi[3]; };
+    std::vector<BoundsEntry> bounds_cache;
 };
 
 extern std::atomic<long long> g_pcr_launches;
@@ -164,15 +167,16 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
     const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
     const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
     const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
-    float best = r2;
-    int bidx = -1;
+    // best (d2, idx) as ONE 64-bit key (fp32 bits of d2 >= 0 order like the value; index in the low word): the
+    // lexicographic tie rule D2 becomes a branch-free unsigned compare.  Start key = (r2, 0): only d2 < r2 beats it.
+    typedef unsigned long long u64k;
+    const uint32_t r2bits = __float_as_uint(r2);
+    u64k bkey = ((u64k)r2bits) << 32;
     if (seed >= 0) {
         const float4 p = __ldg(tgt_orig + seed);
         const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-        if (d2 < r2) {
-            best = d2;
-            bidx = seed;
-        }
+        const u64k k = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)seed;
+        bkey = k < bkey ? k : bkey;
     }
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     if (x0 <= x1) {
@@ -188,6 +192,7 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
             const int dz = (o == 0) ? 0 : ((o - 1) < 3 ? (o - 2) : ((o - 1) < 5 ? ((o - 1) == 3 ? -1 : 1) : (o - 7)));
             const int y = cy + dy, z = cz + dz;
             if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+            const float best = __uint_as_float((uint32_t)(bkey >> 32));
             if (o > 0) {
                 const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
                 const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
@@ -204,16 +209,14 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
             for (uint32_t k = b; k < e; k++) {
                 const float4 p = __ldg(g.sorted + k);
                 const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                const int idx = __float_as_int(p.w);
-                if (d2 < best || (d2 == best && bidx >= 0 && idx < bidx)) {
-                    best = d2;
-                    bidx = idx;
-                }
+                const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                bkey = key < bkey ? key : bkey;
             }
         }
     }
-    *d2_out = best;
-    return bidx;
+    const uint32_t hi = (uint32_t)(bkey >> 32);
+    *d2_out = __uint_as_float(hi);
+    return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
 }
 
 __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {

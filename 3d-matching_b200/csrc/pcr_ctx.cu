@@ -56,6 +56,7 @@ int pcr_pow2ceil_exp(double x) {
 }
 
 void pcr_arena_reset(pcr_ctx *ctx) {
+    ctx->bounds_cache.clear();  // caller buffers may have changed since the previous call
     // keep only the largest block; free the rest so the arena converges to one block
     if (ctx->blocks.size() > 1) {
         size_t total = 0;

@@ -47,6 +47,11 @@ __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, 
 }
 
 int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]) {
+    for (const auto &e : ctx->bounds_cache)
+        if (e.ptr == (const void *)pts && e.n == n) {  // same buffer earlier in this call: no second reduction + sync
+            for (int d = 0; d < 3; d++) { lo[d] = e.lo[d]; hi[d] = e.hi[d]; }
+            return PCR_OK;
+        }
     PCR_ALLOC(b, int, 8);
     {
     KScope ks(ctx, KC_BOUNDS, 16.0 * n);
@@ -59,10 +64,14 @@ int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3])
     int *hb = (int *)ctx->pinned;
     PCR_CUDA(cudaMemcpyAsync(hb, b, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    pcr_ctx::BoundsEntry e;
+    e.ptr = pts;
+    e.n = n;
     for (int d = 0; d < 3; d++) {
-        lo[d] = ord2f_host(hb[d]);
-        hi[d] = ord2f_host(hb[3 + d]);
+        lo[d] = e.lo[d] = ord2f_host(hb[d]);
+        hi[d] = e.hi[d] = ord2f_host(hb[3 + d]);
     }
+    ctx->bounds_cache.push_back(e);
     return PCR_OK;
 }
 

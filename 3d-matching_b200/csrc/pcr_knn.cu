@@ -224,30 +224,39 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__rest
     u64 *buf = sbuf[warp];
     for (int q = blockIdx.x * KNN_WARPS + warp; q < n; q += gridDim.x * KNN_WARPS) {
         const float4 p = __ldg(pts + q);
+        // lane l < 9 accumulates cumulant l = A*B with A, B in {1, x, y, z}; operands are chosen with fp32 value
+        // selects (no divergent switch) and x*1.0 is exact, so lanes 0..2 still add the bare coordinate
+        const int ia = lane < 3 ? lane + 1 : (lane < 6 ? 1 : (lane < 8 ? 2 : 3));
+        const int ib = lane < 3 ? 0 : (lane < 6 ? lane - 2 : (lane < 8 ? lane - 4 : 3));
         int c;
+        double cu = 0.0;
         if (max_nn <= 32) {  // warp-uniform
             u64 mine;
             c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
-            buf[lane] = mine;
-            __syncwarp();
+            // lane k fetches neighbour k (all gathers in flight together); the ordered sum then reads them by shuffle
+            float4 pk = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < c) pk = __ldg(pts + (int)(uint32_t)(mine & 0xffffffffull));
+            if (c >= 3) {
+                for (int k = 0; k < c; k++) {
+                    const float x = __shfl_sync(0xffffffffu, pk.x, k), y = __shfl_sync(0xffffffffu, pk.y, k);
+                    const float z = __shfl_sync(0xffffffffu, pk.z, k);
+                    const float af = ia == 1 ? x : (ia == 2 ? y : z);
+                    const float bf = ib == 0 ? 1.0f : (ib == 1 ? x : (ib == 2 ? y : z));
+                    cu = cu + (double)af * (double)bf;
+                }
+                cu = cu / (double)c;
+            }
         } else {
             c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
-        }
-        double cu = 0.0;
-        if (c >= 3 && lane < 9) {
-            // lane l accumulates cumulant l = A*B with A, B in {1, x, y, z} chosen by value selects (no divergent
-            // switch); x*1.0 is exact, so lanes 0..2 still add the bare coordinate
-            const int ia = lane < 3 ? lane + 1 : (lane < 6 ? 1 : (lane < 8 ? 2 : 3));
-            const int ib = lane < 3 ? 0 : (lane < 6 ? lane - 2 : (lane < 8 ? lane - 4 : 3));
-            for (int k = 0; k < c; k++) {
-                const int j = (int)(uint32_t)(buf[k] & 0xffffffffull);
-                const float4 pj = __ldg(pts + j);
-                const double x = pj.x, y = pj.y, z = pj.z;
-                const double A = ia == 1 ? x : (ia == 2 ? y : z);
-                const double B = ib == 0 ? 1.0 : (ib == 1 ? x : (ib == 2 ? y : z));
-                cu = cu + A * B;
+            if (c >= 3 && lane < 9) {
+                for (int k = 0; k < c; k++) {
+                    const float4 pj = __ldg(pts + (int)(uint32_t)(buf[k] & 0xffffffffull));
+                    const float af = ia == 1 ? pj.x : (ia == 2 ? pj.y : pj.z);
+                    const float bf = ib == 0 ? 1.0f : (ib == 1 ? pj.x : (ib == 2 ? pj.y : pj.z));
+                    cu = cu + (double)af * (double)bf;
+                }
+                cu = cu / (double)c;
             }
-            cu = cu / (double)c;
         }
         double m[9];
 #pragma unroll
