@@ -148,7 +148,7 @@ struct TcSmem {
     float nb[2][TC_N];
 };
 
-__global__ void __launch_bounds__(128, 1) k_match_tc(const __nv_bfloat16 *__restrict__ a_tiles, int n_a_tiles, int nq,
+__global__ void __launch_bounds__(256, 1) k_match_tc(const __nv_bfloat16 *__restrict__ a_tiles, int n_a_tiles, int nq,
                                                      const __nv_bfloat16 *__restrict__ b_tiles, const float *__restrict__ b_nrm2,
                                                      int n_b_tiles, int n_split,
                                                      int *__restrict__ cand_idx, float *__restrict__ cand_kth) {
@@ -227,12 +227,13 @@ __global__ void __launch_bounds__(128, 1) k_match_tc(const __nv_bfloat16 *__rest
             mbar_wait(&S->bar_mma, par_mma);
             par_mma ^= 1;
             tc_fence_after();
-            // epilogue: thread (warp, lane) owns query row 32*warp + lane = TMEM lane; 256 columns in 8 chunks of 32
+            // epilogue: 8 warps; warp w reads TMEM lane quadrant w % 4 (query row 32*(w%4) + lane) and the column half
+            // w / 4 of the tile (4 chunks of 32 columns), keeping its own top-4 list
             const float *nb = S->nb[buf];
 #pragma unroll 1
-            for (int cch = 0; cch < TC_N / 32; cch++) {
+            for (int cch = (warp >> 2) * 4; cch < (warp >> 2) * 4 + 4; cch++) {
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cch * 32), v);
+                tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cch * 32), v);
                 // scores of the 32 columns, then one min-tree: a chunk that cannot enter the top-4 costs ~2 instr/value
                 float sc[32];
 #pragma unroll
@@ -266,11 +267,12 @@ __global__ void __launch_bounds__(128, 1) k_match_tc(const __nv_bfloat16 *__rest
             tc_fence_before();
             __syncthreads();  // TMEM and this base buffer are free again
         }
-        const int row = at * TC_M + warp * 32 + lane;
+        const int row = at * TC_M + (warp & 3) * 32 + lane;
         if (row < nq) {
-            int *ci = cand_idx + ((size_t)sp * nq + row) * TC_NCAND;
+            const int list = sp * 2 + (warp >> 2);  // two candidate lists (column halves) per base slice
+            int *ci = cand_idx + ((size_t)list * nq + row) * TC_NCAND;
             ci[0] = i0; ci[1] = i1; ci[2] = i2; ci[3] = i3;
-            cand_kth[(size_t)sp * nq + row] = s3;
+            cand_kth[(size_t)list * nq + row] = s3;
         }
     }
     tc_fence_before();
@@ -411,10 +413,12 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
         PCR_TRY(tc_prep(ctx, fb, nb, 1, &B));
     }
     // slices of the base rows so that the grid covers the machine
+    // long column streams keep the top-4 insertions rare: only as many slices as needed to occupy the SMs
     int n_split = 1;
-    while (A.n_tiles * n_split < 2 * ctx->sm_count && n_split * 2 <= B.n_tiles && n_split < 16) n_split *= 2;
-    PCR_ALLOC(cand_idx, int, (size_t)n_split * nq * TC_NCAND);
-    PCR_ALLOC(cand_kth, float, (size_t)n_split * nq);
+    while (A.n_tiles * n_split * 2 <= ctx->sm_count && n_split * 2 <= B.n_tiles && n_split < 4) n_split *= 2;
+    const int n_lists = 2 * n_split;  // each CTA keeps two lists per row (column halves of a tile)
+    PCR_ALLOC(cand_idx, int, (size_t)n_lists * nq * TC_NCAND);
+    PCR_ALLOC(cand_kth, float, (size_t)n_lists * nq);
     PCR_ALLOC(fb_rows, int, (size_t)nq);
     PCR_ALLOC(n_fb, unsigned int, 4);
     PCR_CUDA(cudaMemsetAsync(n_fb, 0, 16, ctx->stream));
@@ -426,15 +430,15 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
     }
     const int items = A.n_tiles * n_split;
     {
-        KScope ks(ctx, KC_NN_FEATURES, 224.0 * ((double)nq + (double)nb * A.n_tiles) + 20.0 * nq * n_split, 1,
+        KScope ks(ctx, KC_NN_FEATURES, 224.0 * ((double)nq + (double)nb * A.n_tiles) + 20.0 * nq * n_lists, 1,
                   2.0 * TC_K * (double)A.n_tiles * TC_M * (double)B.n_tiles * TC_N);
-        k_match_tc<<<min(items, ctx->sm_count), 128, smem, ctx->stream>>>(A.tiles, A.n_tiles, nq, B.tiles, B.nrm2, B.n_tiles, n_split,
+        k_match_tc<<<min(items, ctx->sm_count), 256, smem, ctx->stream>>>(A.tiles, A.n_tiles, nq, B.tiles, B.nrm2, B.n_tiles, n_split,
                                                                           cand_idx, cand_kth);
         PCR_LAUNCHED();
     }
     {
-        KScope ks(ctx, KC_MATCH_MISC, 132.0 * nq * (1 + TC_NCAND * n_split), 2);
-        k_match_recheck<<<div_up((long long)nq * 32, 128), 128, 0, ctx->stream>>>(fq, nq, fb, nb, cand_idx, cand_kth, n_split, B.max_bits, nn, fb_rows,
+        KScope ks(ctx, KC_MATCH_MISC, 132.0 * nq * (1 + TC_NCAND * n_lists), 2);
+        k_match_recheck<<<div_up((long long)nq * 32, 128), 128, 0, ctx->stream>>>(fq, nq, fb, nb, cand_idx, cand_kth, n_lists, B.max_bits, nn, fb_rows,
                                                                   n_fb);
         PCR_LAUNCHED();
         k_match_fallback<<<ctx->sm_count * 4, FB_THREADS, 0, ctx->stream>>>(fq, fb, nb, fb_rows, n_fb, nn);

@@ -416,8 +416,12 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     if (count > (1LL << 30)) return pcr_fail(ctx, PCR_ERR_INVALID, "wave too large");
     const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
     PCR_ALLOC(surv, Survivor, (size_t)count);
-    PCR_ALLOC(counters, unsigned int, 4);
-    PCR_ALLOC(recs, pcr_hyp_record, (size_t)cap);
+    // counters and records share one buffer so that the common case (few records) needs ONE D2H copy + sync
+    constexpr int FIRST = 64;
+    unsigned char *hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)cap);
+    if (!hdr) return PCR_ERR_OOM;
+    unsigned int *counters = (unsigned int *)hdr;
+    pcr_hyp_record *recs = (pcr_hyp_record *)(hdr + 16);
     PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
     {
         KScope ks(ctx, KC_RANSAC_GENERATE, 120.0 * (double)count);
@@ -435,9 +439,11 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
-    unsigned int *hc = (unsigned int *)ctx->pinned;
-    PCR_CUDA(cudaMemcpyAsync(hc, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned char *hp = (unsigned char *)ctx->pinned;
+    const int first = cap < FIRST ? cap : FIRST;
+    PCR_CUDA(cudaMemcpyAsync(hp, hdr, 16 + sizeof(pcr_hyp_record) * (size_t)first, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const unsigned int *hc = (const unsigned int *)hp;
     *n_surv_host = hc[0];
     // algorithmic bytes of the validation launch: per survivor 16 M_s (source) + 16 M_t (target) + 8 C (pairs)
     if (ctx->profiling && pend_idx < ctx->pending.size())
@@ -448,8 +454,13 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     if (nrec > (unsigned int)cap)
         return pcr_fail(ctx, PCR_ERR_INVALID, "ransac wave produced %u records, capacity %d", nrec, cap);
     if (nrec) {
-        PCR_CUDA(cudaMemcpyAsync(recs_host, recs, sizeof(pcr_hyp_record) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
-        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const unsigned int got = nrec < (unsigned int)first ? nrec : (unsigned int)first;
+        memcpy(recs_host, hp + 16, sizeof(pcr_hyp_record) * got);
+        if (nrec > got) {
+            PCR_CUDA(cudaMemcpyAsync(recs_host + got, recs + got, sizeof(pcr_hyp_record) * (nrec - got), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         std::sort(recs_host, recs_host + nrec, [](const pcr_hyp_record &a, const pcr_hyp_record &b) { return a.hyp < b.hyp; });
     }
     *n_recs_host = (int)nrec;
