@@ -233,19 +233,23 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__rest
         if (max_nn <= 32) {  // warp-uniform
             u64 mine;
             c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
-            // lane k fetches neighbour k (all gathers in flight together); the ordered sum then reads them by shuffle
-            float4 pk = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < c) pk = __ldg(pts + (int)(uint32_t)(mine & 0xffffffffull));
-            if (c >= 3) {
-                for (int k = 0; k < c; k++) {
-                    const float x = __shfl_sync(0xffffffffu, pk.x, k), y = __shfl_sync(0xffffffffu, pk.y, k);
-                    const float z = __shfl_sync(0xffffffffu, pk.z, k);
-                    const float af = ia == 1 ? x : (ia == 2 ? y : z);
-                    const float bf = ib == 0 ? 1.0f : (ib == 1 ? x : (ib == 2 ? y : z));
-                    cu = cu + (double)af * (double)bf;
-                }
+            // lane k fetches neighbour k (all gathers in flight together) and writes its nine products to shared
+            // memory; lane l < 9 then adds column l in neighbour order (the reference's sequential cumulants)
+            double *prod = reinterpret_cast<double *>(buf);
+            if (lane < c) {
+                const float4 pk = __ldg(pts + (int)(uint32_t)(mine & 0xffffffffull));
+                const double x = pk.x, y = pk.y, z = pk.z;
+                double *d = prod + lane * 9;
+                d[0] = x; d[1] = y; d[2] = z;
+                d[3] = x * x; d[4] = x * y; d[5] = x * z;
+                d[6] = y * y; d[7] = y * z; d[8] = z * z;
+            }
+            __syncwarp();
+            if (c >= 3 && lane < 9) {
+                for (int k = 0; k < c; k++) cu = cu + prod[k * 9 + lane];
                 cu = cu / (double)c;
             }
+            __syncwarp();
         } else {
             c = warp_knn_hybrid(g, p.x, p.y, p.z, r2, max_nn, buf, lane);
             if (c >= 3 && lane < 9) {
