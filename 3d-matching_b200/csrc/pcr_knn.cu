@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx
                                               const int *__restrict__ cnt, int max_nn,
                                               const double *__restrict__ spfh, float *__restrict__ out) {
     __shared__ double sval[4][FPFH_CHUNK][33];
+    __shared__ double sdist[4][FPFH_CHUNK], srinv[4][FPFH_CHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double (*val)[33] = sval[warp];
     for (int i = blockIdx.x * 4 + warp; i < n; i += gridDim.x * 4) {
@@ -479,11 +480,24 @@ __global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx
         double sum = 0.0;           // lanes 0..2: normaliser of block `lane`
         for (int k0 = 1; k0 < c; k0 += FPFH_CHUNK) {
             const int nk = min(FPFH_CHUNK, c - k0);
+            // One correctly rounded reciprocal per neighbour, then every quotient SPFH/d2 by Markstein's sequence
+            // q0 = a*r, rem = fma(-b, q0, a), q = fma(rem, r, q0): with r = RN(1/b) this IS the correctly rounded a/b
+            // unless b's significand is all ones — impossible here, b is an fp32 value widened to fp64.  33 divisions
+            // per neighbour become 1 division + 33 x 3 multiply-adds with identical bits (checked by the parity tests).
+            if (lane < nk) {
+                const double dist = (double)d2[(size_t)i * max_nn + k0 + lane];
+                sdist[warp][lane] = dist;
+                srinv[warp][lane] = dist == 0.0 ? 0.0 : 1.0 / dist;
+            }
+            __syncwarp();
             for (int e = lane; e < nk * 33; e += 32) {
                 const int kk = e / 33, j = e - kk * 33;
-                const double dist = (double)d2[(size_t)i * max_nn + k0 + kk];
+                const double b = sdist[warp][kk], r = srinv[warp][kk];
+                const double a = spfh[(size_t)idx[(size_t)i * max_nn + k0 + kk] * 33 + j];
+                const double q0 = a * r;
+                const double rem = __fma_rn(-b, q0, a);
                 // a zero distance (duplicate point) is skipped by the reference; adding +0.0 is the same bits
-                val[kk][j] = dist == 0.0 ? 0.0 : spfh[(size_t)idx[(size_t)i * max_nn + k0 + kk] * 33 + j] / dist;
+                val[kk][j] = b == 0.0 ? 0.0 : __fma_rn(rem, r, q0);
             }
             __syncwarp();
             for (int kk = 0; kk < nk; kk++) {
