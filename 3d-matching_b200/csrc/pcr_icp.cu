@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(256) k_icp_nn(const float4 *__restrict__ src, 
         const float4 p = __ldg(src + i);
         const float3 q = xform_pt(sT, p.x, p.y, p.z);
         float d2;
+        // the previous pass's correspondence seeds the search bound (worth ~3 %: the home row alone already gives a
+        // tight bound); the result does not depend on it
         const int j = grid_nn1_seeded(g, q.x, q.y, q.z, r2, seed[i], tgt, &d2);
         seed[i] = j;
         d2s[i] = d2;

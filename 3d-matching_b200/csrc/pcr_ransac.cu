@@ -524,7 +524,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
     std::vector<pcr_hyp_record> recs;
-    int64_t begin = 0, wave = 4096;
+    int64_t begin = 0, wave = 8192;  // first wave small enough for the common early exit, then x4 to fill the GPU
     int64_t survivors = 0;
     while (begin < max_iter && begin < res->est_k) {
         const int64_t end = std::min<int64_t>(max_iter, begin + wave);
@@ -544,7 +544,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
         pcr_ransac_scan(recs.data(), nrec, begin, end, c, ms, confidence, w.k_d, res, &stop);
         begin = end;
         if (stop) break;
-        if (wave < (1 << 20)) wave *= 2;
+        if (wave < (1 << 20)) wave *= 4;
     }
     res->survivors = survivors;
     res->k_d = w.k_d;
