@@ -185,19 +185,36 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
         const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
         const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
         const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
+        // per-axis squared slab distances (in cells, shrunk by the 1e-4 slack) to the -1 / 0 / +1 neighbour slabs
+        const float ry = fyf - (float)cy, rz = fzf - (float)cz;  // position inside the home cell, [0,1) when inside the grid
+        const float ym = fmaxf(ry - 1e-4f, 0.0f), yp = fmaxf(1.0f - ry - 1e-4f, 0.0f);
+        const float zm = fmaxf(rz - 1e-4f, 0.0f), zp = fmaxf(1.0f - rz - 1e-4f, 0.0f);
+        const float ey2[3] = {ym * ym * h2, 0.0f, yp * yp * h2};
+        const float ez2[3] = {zm * zm * h2, 0.0f, zp * zp * h2};
+        // visiting order: home row first, then the 8 others; (dy+1, dz+1) packed 2 bits each, 9 entries
+        //   o:      0      1      2      3      4      5      6      7      8
+        //   dy+1:   1      0      0      0      1      1      2      2      2
+        //   dz+1:   1      0      1      2      0      2      0      1      2
+        const uint32_t DYP = 1u | (0u << 2) | (0u << 4) | (0u << 6) | (1u << 8) | (1u << 10) | (2u << 12) | (2u << 14) | (2u << 16);
+        const uint32_t DZP = 1u | (0u << 2) | (1u << 4) | (2u << 6) | (0u << 8) | (2u << 10) | (0u << 12) | (1u << 14) | (2u << 16);
+        const bool inside = (cy >= 0 && cy < g.ny && cz >= 0 && cz < g.nz);
 #pragma unroll 1
         for (int o = 0; o < 9; o++) {
-            // o = 0 is the home row, then the 8 others
-            const int dy = (o == 0) ? 0 : ((o - 1) < 3 ? -1 : ((o - 1) < 5 ? 0 : 1));
-            const int dz = (o == 0) ? 0 : ((o - 1) < 3 ? (o - 2) : ((o - 1) < 5 ? ((o - 1) == 3 ? -1 : 1) : (o - 7)));
-            const int y = cy + dy, z = cz + dz;
+            const int iy = (DYP >> (2 * o)) & 3, iz = (DZP >> (2 * o)) & 3;
+            const int y = cy + iy - 1, z = cz + iz - 1;
             if (y < y0 || y > y1 || z < z0 || z > z1) continue;
             const float best = __uint_as_float((uint32_t)(bkey >> 32));
             if (o > 0) {
-                const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
-                const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
-                const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
-                if ((sy * sy + sz * sz) * h2 > best) continue;
+                float lb;
+                if (inside) {
+                    lb = (iy == 0 ? ey2[0] : (iy == 1 ? 0.0f : ey2[2])) + (iz == 0 ? ez2[0] : (iz == 1 ? 0.0f : ez2[2]));
+                } else {  // query outside the grid: general slab distance
+                    const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
+                    const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
+                    const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
+                    lb = (sy * sy + sz * sz) * h2;
+                }
+                if (lb > best) continue;
             }
             // cells of the row that can hold a point within the current best distance (in cell units, padded)
             const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
@@ -216,6 +233,60 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
     }
     const uint32_t hi = (uint32_t)(bkey >> 32);
     *d2_out = __uint_as_float(hi);
+    return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
+}
+
+// Search variant that also returns a CERTIFICATE for later reuse: *second_lb is a lower bound of the squared distance
+// from the query to every target point other than the returned nearest one.  All points within the certificate
+// radius sqrt(rc2) (>= the current best distance) are examined, so second_lb = min(second smallest examined d2,
+// rc2 * (1 - 2e-4)).  The nearest neighbour itself is found exactly as by grid_nn1 (same key order, same radius rule).
+__device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, float qz, float r2, float rc2,
+                                             float *d2_out, float *second_lb) {
+    typedef unsigned long long u64k;
+    const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
+    const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
+    const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
+    const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
+    const uint32_t r2bits = __float_as_uint(r2);
+    u64k bkey = ((u64k)0x7f800000u) << 32;  // +inf: the best over ALL examined points (the radius rule is applied at the end)
+    float second = INFINITY;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    if (x0 <= x1) {
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+        const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
+        const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
+        const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
+#pragma unroll 1
+        for (int o = 0; o < 9; o++) {
+            const int y = cy + o / 3 - 1, z = cz + o % 3 - 1;
+            if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+            // prune with max(min(best, r2), rc2): everything inside the certificate radius is examined
+            const float best = fminf(__uint_as_float((uint32_t)(bkey >> 32)), r2);
+            const float lim = fmaxf(best, rc2);
+            const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
+            const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
+            const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
+            if ((sy * sy + sz * sz) * h2 > lim) continue;
+            const float rc = sqrtf(lim) * inv_hf * 1.0001f + 1e-4f;
+            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
+            if (xa > xb) continue;
+            const long long row = ((long long)z * g.ny + y) * g.nx;
+            const uint32_t b = __ldg(g.start + row + xa);
+            const uint32_t e = __ldg(g.start + row + xb + 1);
+            for (uint32_t k = b; k < e; k++) {
+                const float4 p = __ldg(g.sorted + k);
+                const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                const bool lt = key < bkey;
+                second = fminf(second, lt ? __uint_as_float((uint32_t)(bkey >> 32)) : d2);
+                bkey = lt ? key : bkey;
+            }
+        }
+    }
+    const uint32_t hi = (uint32_t)(bkey >> 32);
+    *d2_out = __uint_as_float(hi);
+    *second_lb = fminf(second, rc2 * (1.0f - 2e-4f));
     return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
 }
 

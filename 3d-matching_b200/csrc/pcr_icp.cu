@@ -141,23 +141,81 @@ __device__ void icp_finish_pass(IcpState *S, int ns) {
 
 constexpr int ICP_THREADS = 256;
 
-// NN half of a pass.  seed[i] (Morton order) holds the previous pass's correspondence on entry (-1 in pass 0; it
-// only tightens the initial search bound) and this pass's on exit; d2s[i] the fp32 squared distance.
+// Correspondence of one transformed source point q (index i in Morton order): certified reuse or full search; keeps
+// seed[i] / cert[i] up to date (see k_icp_nn).  Returns the target index or -1 and the fp32 squared distance.
+__device__ __forceinline__ int icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, float3 q, float r2, float rc2, int pass,
+                                            int i, int *__restrict__ seed, float4 *__restrict__ cert, float *d2_out) {
+    const int j_old = seed[i];
+    if (j_old >= 0 && pass >= 3) {
+        const float4 c = cert[i];
+        if (c.w > 0.0f) {
+            const float4 t = __ldg(tgt + j_old);
+            const float d1 = dist2f(q.x, q.y, q.z, t.x, t.y, t.z);
+            const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
+            const float delta = sqrtf((mx * mx + my * my) + mz * mz);
+            if ((sqrtf(d1) + delta) * 1.00002f < sqrtf(c.w) * 0.99998f) {
+                const int j = d1 < r2 ? j_old : -1;
+                seed[i] = j;
+                *d2_out = d1;
+                return j;
+            }
+        }
+    }
+    float d2, second = 0.0f;
+    int j;
+    if (pass >= 2) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, rc2, &d2, &second);
+    else j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+    seed[i] = j;
+    if (pass >= 2) cert[i] = make_float4(q.x, q.y, q.z, j >= 0 ? second : 0.0f);
+    *d2_out = d2;
+    return j;
+}
+
+// point-to-plane normal equations of one correspondence, int64 fixed point (rule D5)
+__device__ __forceinline__ void icp_accumulate(long long *acc, float3 q, float d2, float4 tp, float4 np, double scJJ, double scJr,
+                                               double scd) {
+    const double sx = q.x, sy = q.y, sz = q.z;
+    const double nx = np.x, ny = np.y, nz = np.z;
+    const double r = ((sx - (double)tp.x) * nx + (sy - (double)tp.y) * ny) + (sz - (double)tp.z) * nz;
+    double J[6];
+    J[0] = sy * nz - sz * ny;
+    J[1] = sz * nx - sx * nz;
+    J[2] = sx * ny - sy * nx;
+    J[3] = nx;
+    J[4] = ny;
+    J[5] = nz;
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int c = a; c < 6; c++) acc[e++] += fixed_ll(J[a] * J[c], scJJ);
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[21 + a] += fixed_ll(J[a] * r, scJr);
+    acc[27] += 1;
+    acc[28] += fixed_ll((double)d2, scd);
+}
+
+// NN half of a pass.  Per source point (Morton order) the state is seed[i] = current correspondence (-1: none) and
+// cert[i] = (query position at the last full search, lower bound of the squared distance to every OTHER target point).
+// A pass first tries to CERTIFY the previous correspondence j: if dist(q', t_j) + |q' - q_ref| is below the distance
+// bound of all other points (triangle inequality, 2e-5 relative slack >> fp32 rounding), j is still the unique
+// nearest neighbour, so d2 = fp32 dist2(q', t_j) is exactly what the search would return and the search is skipped.
+// Otherwise the full grid search runs (from pass 2 on it also refreshes the certificate).  Results are identical to
+// searching every pass; late ICP passes, where the update is tiny, certify nearly every point.
 __global__ void __launch_bounds__(256) k_icp_nn(const float4 *__restrict__ src, int ns, Grid g, const float4 *__restrict__ tgt,
                                                 float r2, const IcpState *__restrict__ S, int *__restrict__ seed,
-                                                float *__restrict__ d2s) {
+                                                float *__restrict__ d2s, float4 *__restrict__ cert) {
     if (S->done) return;
     __shared__ double sT[12];
     if (threadIdx.x < 12) sT[threadIdx.x] = S->T[threadIdx.x];
+    const int pass = S->pass;
     __syncthreads();
+    const float rc2 = 0.64f * (float)(g.h * g.h);  // certificate radius 0.8 cell
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
         const float4 p = __ldg(src + i);
         const float3 q = xform_pt(sT, p.x, p.y, p.z);
         float d2;
-        // the previous pass's correspondence seeds the search bound (worth ~3 %: the home row alone already gives a
-        // tight bound); the result does not depend on it
-        const int j = grid_nn1_seeded(g, q.x, q.y, q.z, r2, seed[i], tgt, &d2);
-        seed[i] = j;
+        const int j = icp_point_nn(g, tgt, q, r2, rc2, pass, i, seed, cert, &d2);
         d2s[i] = d2;
     }
 }
@@ -185,27 +243,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_accum(const float4 *__restr
             const float4 p = __ldg(src + i);
             const float3 q = xform_pt(T, p.x, p.y, p.z);
             const float d2 = d2s[i];
-            const float4 tp = __ldg(tgt + j);
-            const float4 np = __ldg(nrm + j);
-            const double sx = q.x, sy = q.y, sz = q.z;
-            const double nx = np.x, ny = np.y, nz = np.z;
-            const double r = ((sx - (double)tp.x) * nx + (sy - (double)tp.y) * ny) + (sz - (double)tp.z) * nz;
-            double J[6];
-            J[0] = sy * nz - sz * ny;
-            J[1] = sz * nx - sx * nz;
-            J[2] = sx * ny - sy * nx;
-            J[3] = nx;
-            J[4] = ny;
-            J[5] = nz;
-            int e = 0;
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = a; c < 6; c++) acc[e++] += fixed_ll(J[a] * J[c], scJJ);
-#pragma unroll
-            for (int a = 0; a < 6; a++) acc[21 + a] += fixed_ll(J[a] * r, scJr);
-            acc[27] += 1;
-            acc[28] += fixed_ll((double)d2, scd);
+            icp_accumulate(acc, q, d2, __ldg(tgt + j), __ldg(nrm + j), scJJ, scJr, scd);
         }
     }
     // block reduction (integer sums: any order gives the same bits)
@@ -313,6 +351,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_ALLOC(dS, IcpState, 1);
     PCR_ALLOC(seed, int, (size_t)ns);
     PCR_ALLOC(d2s, float, (size_t)ns);
+    PCR_ALLOC(cert, float4, (size_t)ns);
     PCR_CUDA(cudaMemsetAsync(seed, 0xff, sizeof(int) * (size_t)ns, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     const float r2 = (float)(max_dist * max_dist);
@@ -322,7 +361,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     {
         KScope ks(ctx, KC_ICP_PASS, 16.0 * ns + 32.0 * nt + 4.0 * ns, max_iter + 1);
         for (int pass = 0; pass <= max_iter; pass++) {
-            k_icp_nn<<<nn_blocks, 256, 0, ctx->stream>>>(src_sorted, ns, g, tgt, r2, dS, seed, d2s);
+            k_icp_nn<<<nn_blocks, 256, 0, ctx->stream>>>(src_sorted, ns, g, tgt, r2, dS, seed, d2s, cert);
             PCR_LAUNCHED();
             k_icp_accum<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, tgt, nrm, dS, seed, d2s);
             PCR_LAUNCHED();
