@@ -236,58 +236,63 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
     return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
 }
 
-// Search variant that also returns a CERTIFICATE for later reuse: *second_lb is a lower bound of the squared distance
-// from the query to every target point other than the returned nearest one.  All points within the certificate
-// radius sqrt(rc2) (>= the current best distance) are examined, so second_lb = min(second smallest examined d2,
-// rc2 * (1 - 2e-4)).  The nearest neighbour itself is found exactly as by grid_nn1 (same key order, same radius rule).
-__device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, float qz, float r2, float rc2,
-                                             float *d2_out, float *second_lb) {
+// Search variant that also returns a CERTIFICATE for later reuse.  It examines EVERY point of the 3x3x3 cell block
+// around the query (no pruning: the row ranges are fetched three rows per round trip), i.e. every target point within
+// one cell size h of the query, and keeps the two smallest keys (d2, index) and the third smallest d2:
+//   *d2_out   smallest examined d2 (+inf if the block is empty) — also when it is not below r2, so that a
+//             "no correspondence" result carries a certificate too;
+//   *other_lb lower bound of the squared distance from the query to every target point OTHER than the nearest
+//             examined one: min(second smallest examined d2, h^2 (1 - 2e-4));
+//   *j2, *third_lb the second nearest examined point (-1 if none) and the same kind of bound for every point other
+//             than the nearest two.
+// The nearest neighbour itself is found exactly as by grid_nn1 (same key order, same radius rule).
+__device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out,
+                                             float *other_lb, int *j2, float *third_lb) {
     typedef unsigned long long u64k;
     const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
     const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
     const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
     const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
     const uint32_t r2bits = __float_as_uint(r2);
-    u64k bkey = ((u64k)0x7f800000u) << 32;  // +inf: the best over ALL examined points (the radius rule is applied at the end)
-    float second = INFINITY;
+    const u64k KINF = ((u64k)0x7f800000u) << 32;  // +inf: keys over ALL examined points (the radius rule is applied at the end)
+    u64k k1 = KINF, k2 = KINF;
+    float third = INFINITY;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     if (x0 <= x1) {
-        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-        const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
-        const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
-        const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
 #pragma unroll 1
-        for (int o = 0; o < 9; o++) {
-            const int y = cy + o / 3 - 1, z = cz + o % 3 - 1;
-            if (y < y0 || y > y1 || z < z0 || z > z1) continue;
-            // prune with max(min(best, r2), rc2): everything inside the certificate radius is examined
-            const float best = fminf(__uint_as_float((uint32_t)(bkey >> 32)), r2);
-            const float lim = fmaxf(best, rc2);
-            const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
-            const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
-            const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
-            if ((sy * sy + sz * sz) * h2 > lim) continue;
-            const float rc = sqrtf(lim) * inv_hf * 1.0001f + 1e-4f;
-            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
-            if (xa > xb) continue;
-            const long long row = ((long long)z * g.ny + y) * g.nx;
-            const uint32_t b = __ldg(g.start + row + xa);
-            const uint32_t e = __ldg(g.start + row + xb + 1);
-            for (uint32_t k = b; k < e; k++) {
-                const float4 p = __ldg(g.sorted + k);
-                const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
-                const bool lt = key < bkey;
-                second = fminf(second, lt ? __uint_as_float((uint32_t)(bkey >> 32)) : d2);
-                bkey = lt ? key : bkey;
+        for (int dz = -1; dz <= 1; dz++) {
+            const int z = cz + dz;
+            if (z < 0 || z >= g.nz) continue;
+            uint32_t rb[3], re[3];
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int y = cy + dy;
+                const bool ok = y >= 0 && y < g.ny;
+                const long long row = ((long long)z * g.ny + (ok ? y : 0)) * g.nx;
+                rb[dy + 1] = ok ? __ldg(g.start + row + x0) : 0u;
+                re[dy + 1] = ok ? __ldg(g.start + row + x1 + 1) : 0u;
+            }
+#pragma unroll
+            for (int o = 0; o < 3; o++) {
+                for (uint32_t k = rb[o]; k < re[o]; k++) {
+                    const float4 p = __ldg(g.sorted + k);
+                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                    const bool lt1 = key < k1, lt2 = key < k2;
+                    third = lt2 ? __uint_as_float((uint32_t)(k2 >> 32)) : fminf(third, d2);
+                    k2 = lt1 ? k1 : (lt2 ? key : k2);
+                    k1 = lt1 ? key : k1;
+                }
             }
         }
     }
-    const uint32_t hi = (uint32_t)(bkey >> 32);
+    const uint32_t hi = (uint32_t)(k1 >> 32);
     *d2_out = __uint_as_float(hi);
-    *second_lb = fminf(second, rc2 * (1.0f - 2e-4f));
-    return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
+    const float hlim = (float)(g.h * g.h) * (1.0f - 2e-4f);
+    *other_lb = fminf(__uint_as_float((uint32_t)(k2 >> 32)), hlim);
+    *j2 = k2 < KINF ? (int)(uint32_t)(k2 & 0xffffffffull) : -1;
+    *third_lb = fminf(third, hlim);
+    return hi < r2bits ? (int)(uint32_t)(k1 & 0xffffffffull) : -1;
 }
 
 __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {

@@ -12,12 +12,16 @@
 //                 the Euler-ZYX update, applies the convergence test and publishes the next transform.
 //
 // HBM roofline: 16 B source + 16 B target + 16 B normal + 4 B index = 52 B per point and pass.
+#include <cstdio>
+#include <cstdlib>
+
 #include "pcr_common.cuh"
 
 struct IcpState {
     double T[16];
-    long long acc[32];  // 0..20 JtJ upper triangle (row-major), 21..26 Jtr, 27 count, 28 sum d2
-    unsigned int ticket;
+    long long acc3[3][32];  // triple-buffered: 0..20 JtJ upper triangle (row-major), 21..26 Jtr, 27 count, 28 sum d2
+    unsigned int bar;       // grid-barrier arrival counter
+    int dbgflags;           // PCR_ICP_DBG (development only): 1 skip accumulate, 2 skip rows, 4 skip NN, 8 skip xform
     int pass;
     int done;
     int iterations;
@@ -27,12 +31,16 @@ struct IcpState {
     double fitness, rmse;
     long long count, sumq;
     double rel_fit, rel_rmse;
-    double sc_JJ, sc_Jr, sc_d;       // 2^k scales
-    double isc_JJ, isc_Jr, isc_d;    // 2^-k
+    double sc_J, sc_R, sc_d;         // 2^(kq - e_J), 2^(kq - e_R), 2^k_d
+    double isc_JJ, isc_Jr, isc_d;    // 2^-2(kq - e_J), 2^-((kq - e_J) + (kq - e_R)), 2^-k_d
     double T_out[16];
+    long long dbgmax[64];  // per-pass slowest CTA loop
+    long long dbgfin[64];  // per-pass slowest CTA finish
+    long long dbgp[64];  // per-pass loop cycles of CTA 0 (first 64 passes)
+    long long dbg[4];  // clock cycles of CTA 0: point loop, reduction + barrier, end-of-pass logic (PCR_ICP_TRACE=1 prints them)
 };
 
-__device__ int ldlt6_solve_dev(const double A[6][6], const double *b, double *x) {
+__device__ __forceinline__ int ldlt6_solve_dev(const double (*A)[6], const double *b, double *x) {
     double L[6][6], d[6], y[6];
     bool bad = false;
 #pragma unroll
@@ -77,42 +85,43 @@ __device__ int ldlt6_solve_dev(const double A[6][6], const double *b, double *x)
     return 0;
 }
 
-// runs in ONE thread of the last block of a pass
-__device__ void icp_finish_pass(IcpState *S, int ns) {
-    const long long cnt = S->acc[27], sumq = S->acc[28];
+// Per-CTA replica of the loop state.  Every CTA runs the (deterministic) end-of-pass logic redundantly on the same
+// 29 integer sums, so all CTAs hold bit-identical transforms and stop flags without a second grid barrier.
+struct IcpLocal {
+    double T[16];
+    double prev_fit, prev_rmse, fitness, rmse;
+    long long count, sumq;
+    int pass, done, iterations, converged;
+};
+
+// end-of-pass logic (ONE thread per CTA): convergence test, 6x6 solve, Euler-ZYX update, T <- U T
+// fA / fb: the normal equations A x = b already converted to fp64 (shared memory, filled by 27 threads)
+__device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, const double (*fA)[6], const double *fb,
+                                             double isc_d, double rel_fit, double rel_rmse, int max_iter, int ns) {
+    const long long cnt = acc[27], sumq = acc[28];
     const double fit = (double)cnt / (double)ns;
-    const double rmse = cnt > 0 ? sqrt(((double)sumq * S->isc_d) / (double)cnt) : 0.0;
-    S->fitness = fit;
-    S->rmse = rmse;
-    S->count = cnt;
-    S->sumq = sumq;
-    for (int i = 0; i < 16; i++) S->T_out[i] = S->T[i];
-    const int pass = S->pass;
+    const double rmse = cnt > 0 ? sqrt(((double)sumq * isc_d) / (double)cnt) : 0.0;
+    L->fitness = fit;
+    L->rmse = rmse;
+    L->count = cnt;
+    L->sumq = sumq;
+    const int pass = L->pass;
     bool stop = false;
-    if (pass > 0 && fabs(S->prev_fit - fit) < S->rel_fit && fabs(S->prev_rmse - rmse) < S->rel_rmse) {
-        S->converged = 1;
+    if (pass > 0 && fabs(L->prev_fit - fit) < rel_fit && fabs(L->prev_rmse - rmse) < rel_rmse) {
+        L->converged = 1;
         stop = true;
     }
-    if (!stop && pass >= S->max_iter) stop = true;
+    if (!stop && pass >= max_iter) stop = true;
     if (stop) {
-        S->done = 1;
+        L->done = 1;
     } else {
-        S->prev_fit = fit;
-        S->prev_rmse = rmse;
+        L->prev_fit = fit;
+        L->prev_rmse = rmse;
         double U[16];
         for (int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
         if (cnt > 0) {
-            double A[6][6], b[6], x[6];
-            int e = 0;
-            for (int a = 0; a < 6; a++)
-                for (int c = a; c < 6; c++) {
-                    const double v = (double)S->acc[e] * S->isc_JJ;
-                    A[a][c] = v;
-                    A[c][a] = v;
-                    e++;
-                }
-            for (int a = 0; a < 6; a++) b[a] = -((double)S->acc[21 + a] * S->isc_Jr);
-            if (ldlt6_solve_dev(A, b, x) == 0) {
+            double x[6];
+            if (ldlt6_solve_dev(fA, fb, x) == 0) {
                 double sa, ca, sb, cb, sg, cg;
                 pcr_sincos(x[0], &sa, &ca);
                 pcr_sincos(x[1], &sb, &cb);
@@ -125,160 +134,323 @@ __device__ void icp_finish_pass(IcpState *S, int ns) {
         double Tn[16];
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 4; j++) {
-                double v = (U[4 * i] * S->T[j] + U[4 * i + 1] * S->T[4 + j]) + U[4 * i + 2] * S->T[8 + j];
+                double v = (U[4 * i] * L->T[j] + U[4 * i + 1] * L->T[4 + j]) + U[4 * i + 2] * L->T[8 + j];
                 if (j == 3) v = v + U[4 * i + 3];
                 Tn[4 * i + j] = v;
             }
         Tn[12] = Tn[13] = Tn[14] = 0.0;
         Tn[15] = 1.0;
-        for (int i = 0; i < 16; i++) S->T[i] = Tn[i];
-        S->iterations = pass + 1;
+        for (int i = 0; i < 16; i++) L->T[i] = Tn[i];
+        L->iterations = pass + 1;
     }
-    S->pass = pass + 1;
-    for (int i = 0; i < 32; i++) S->acc[i] = 0;
-    S->ticket = 0;
+    L->pass = pass + 1;
 }
 
 constexpr int ICP_THREADS = 256;
+constexpr int ICP_WARPS = ICP_THREADS / 32;
 
 // Correspondence of one transformed source point q (index i in Morton order): certified reuse or full search; keeps
-// seed[i] / cert[i] up to date (see k_icp_nn).  Returns the target index or -1 and the fp32 squared distance.
-__device__ __forceinline__ int icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, float3 q, float r2, float rc2, int pass,
-                                            int i, int *__restrict__ seed, float4 *__restrict__ cert, float *d2_out) {
-    const int j_old = seed[i];
-    if (j_old >= 0 && pass >= 3) {
+// seed[i] / cert[i] up to date (see k_icp_persist).  Returns the target index or -1 and the fp32 squared distance.
+//
+// cert[i] = (q_ref, w): q_ref is the query position at the last certificate search (grid_nn1_cert, which examines
+// every target point within one cell size h > max_dist of q_ref).
+//   w > 0 : a correspondence j existed; w is a lower bound of the squared distance from q_ref to every OTHER target
+//           point.  For the new position q, with delta = |q - q_ref|: every other point is at least sqrt(w) - delta
+//           away, so if dist(q, t_j) < sqrt(w) - delta then j is still the unique nearest point, and
+//           d2 = fp32 dist2(q, t_j) is exactly what the search would return (the radius rule is re-applied).
+//   w < 0 : no correspondence; -w is a lower bound of the squared distance from q_ref to EVERY target point, so if
+//           sqrt(-w) - delta > max_dist there is still none.
+//   w = 0 : no certificate (passes 0..1 use the cheaper pruned search while the cloud still moves).
+// Near-ties (second nearest almost as close as the nearest: a fraction ~1e-4 of the points, and persistently so once
+// the cloud has stopped moving) would fail that test in every pass, and one such point stalls its whole CTA in a full
+// search.  They take a second tier: cert2[i] = (j2, w3) holds the second nearest point and a lower bound for every
+// point other than the nearest two; j is kept if it beats j2 in the exact (d2, index) key order and beats w3 as above.
+// All bound comparisons carry a 2e-5 relative slack on both sides, orders of magnitude above the fp32 rounding of
+// the distances involved, so a certified answer is always the exact answer.
+__device__ __forceinline__ int icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, float3 q, float r2, float max_dist_f, int pass,
+                                            int i, int *__restrict__ seed, float4 *__restrict__ cert, float2 *__restrict__ cert2,
+                                            float *d2_out) {
+    if (pass >= 3) {
         const float4 c = cert[i];
+        const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
+        const float delta = sqrtf((mx * mx + my * my) + mz * mz);
         if (c.w > 0.0f) {
+            const int j_old = seed[i];
             const float4 t = __ldg(tgt + j_old);
             const float d1 = dist2f(q.x, q.y, q.z, t.x, t.y, t.z);
-            const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
-            const float delta = sqrtf((mx * mx + my * my) + mz * mz);
-            if ((sqrtf(d1) + delta) * 1.00002f < sqrtf(c.w) * 0.99998f) {
-                const int j = d1 < r2 ? j_old : -1;
-                seed[i] = j;
+            // (a certified nearest point that has drifted out of the radius takes the search path, which then
+            // records a "no correspondence" certificate)
+            if (d1 < r2 && (sqrtf(d1) + delta) * 1.00002f < sqrtf(c.w) * 0.99998f) {
                 *d2_out = d1;
-                return j;
+                return j_old;
+            }
+            const float2 c2 = cert2[i];
+            const int j2 = __float_as_int(c2.x);
+            if (j2 >= 0) {
+                typedef unsigned long long u64k;
+                const float4 t2 = __ldg(tgt + j2);
+                const float d2b = dist2f(q.x, q.y, q.z, t2.x, t2.y, t2.z);
+                const u64k ka = (((u64k)__float_as_uint(d1)) << 32) | (uint32_t)j_old;
+                const u64k kb = (((u64k)__float_as_uint(d2b)) << 32) | (uint32_t)j2;
+                const bool a_wins = ka < kb;  // exactly the comparison the search makes between these two
+                const float dw = a_wins ? d1 : d2b;
+                if (dw < r2 && (sqrtf(dw) + delta) * 1.00002f < sqrtf(c2.y) * 0.99998f) {
+                    if (!a_wins) {
+                        // the pair swaps roles (a correspondence that flips under the last-bit jitter of a
+                        // converged transform): w no longer bounds "all points but the nearest", so it is set to
+                        // a value that always defers to this tier; w3 bounds every point outside the pair as before
+                        seed[i] = j2;
+                        cert2[i] = make_float2(__int_as_float(j_old), c2.y);
+                        cert[i] = make_float4(c.x, c.y, c.z, 1.17549435e-38f);
+                    }
+                    *d2_out = dw;
+                    return a_wins ? j_old : j2;
+                }
+            }
+        } else if (c.w < 0.0f) {
+            if ((max_dist_f + delta) * 1.00002f < sqrtf(-c.w) * 0.99998f) {
+                *d2_out = 0.0f;
+                return -1;
             }
         }
     }
-    float d2, second = 0.0f;
+    float d2;
     int j;
-    if (pass >= 2) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, rc2, &d2, &second);
-    else j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
-    seed[i] = j;
-    if (pass >= 2) cert[i] = make_float4(q.x, q.y, q.z, j >= 0 ? second : 0.0f);
+    if (pass >= 2) {
+        float other, third;
+        int j2;
+        j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
+        if (j >= 0) {
+            seed[i] = j;
+            cert[i] = make_float4(q.x, q.y, q.z, other);
+            cert2[i] = make_float2(__int_as_float(j2), third);
+        } else {
+            seed[i] = -1;
+            // nothing inside the radius: every target point is at least min(nearest examined, h) away
+            cert[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
+        }
+    } else {
+        j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+        seed[i] = j;
+    }
     *d2_out = d2;
     return j;
 }
 
-// point-to-plane normal equations of one correspondence, int64 fixed point (rule D5)
-__device__ __forceinline__ void icp_accumulate(long long *acc, float3 q, float d2, float4 tp, float4 np, double scJJ, double scJr,
-                                               double scd) {
-    const double sx = q.x, sy = q.y, sz = q.z;
-    const double nx = np.x, ny = np.y, nz = np.z;
-    const double r = ((sx - (double)tp.x) * nx + (sy - (double)tp.y) * ny) + (sz - (double)tp.z) * nz;
-    double J[6];
-    J[0] = sy * nz - sz * ny;
-    J[1] = sz * nx - sx * nz;
-    J[2] = sx * ny - sy * nx;
-    J[3] = nx;
-    J[4] = ny;
-    J[5] = nz;
-    int e = 0;
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int c = a; c < 6; c++) acc[e++] += fixed_ll(J[a] * J[c], scJJ);
-#pragma unroll
-    for (int a = 0; a < 6; a++) acc[21 + a] += fixed_ll(J[a] * r, scJr);
-    acc[27] += 1;
-    acc[28] += fixed_ll((double)d2, scd);
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-// NN half of a pass.  Per source point (Morton order) the state is seed[i] = current correspondence (-1: none) and
-// cert[i] = (query position at the last full search, lower bound of the squared distance to every OTHER target point).
-// A pass first tries to CERTIFY the previous correspondence j: if dist(q', t_j) + |q' - q_ref| is below the distance
-// bound of all other points (triangle inequality, 2e-5 relative slack >> fp32 rounding), j is still the unique
-// nearest neighbour, so d2 = fp32 dist2(q', t_j) is exactly what the search would return and the search is skipped.
-// Otherwise the full grid search runs (from pass 2 on it also refreshes the certificate).  Results are identical to
-// searching every pass; late ICP passes, where the update is tiny, certify nearly every point.
-__global__ void __launch_bounds__(256) k_icp_nn(const float4 *__restrict__ src, int ns, Grid g, const float4 *__restrict__ tgt,
-                                                float r2, const IcpState *__restrict__ S, int *__restrict__ seed,
-                                                float *__restrict__ d2s, float4 *__restrict__ cert) {
-    if (S->done) return;
-    __shared__ double sT[12];
-    if (threadIdx.x < 12) sT[threadIdx.x] = S->T[threadIdx.x];
-    const int pass = S->pass;
-    __syncthreads();
-    const float rc2 = 0.64f * (float)(g.h * g.h);  // certificate radius 0.8 cell
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(src + i);
-        const float3 q = xform_pt(sT, p.x, p.y, p.z);
-        float d2;
-        const int j = icp_point_nn(g, tgt, q, r2, rc2, pass, i, seed, cert, &d2);
-        d2s[i] = d2;
-    }
-}
-
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_accum(const float4 *__restrict__ src, int ns,
-                                                           const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
-                                                           IcpState *__restrict__ S, const int *__restrict__ seed,
-                                                           const float *__restrict__ d2s) {
-    if (S->done) return;
-    __shared__ double sT[12];
-    __shared__ long long red[ICP_THREADS / 32][29];
-    __shared__ bool is_last;
-    if (threadIdx.x < 12) sT[threadIdx.x] = S->T[threadIdx.x];
-    const double scJJ = S->sc_JJ, scJr = S->sc_Jr, scd = S->sc_d;
-    __syncthreads();
-    const double *T = sT;  // broadcast shared-memory reads keep 24 registers free for the accumulators
-
-    long long acc[29];
-#pragma unroll
-    for (int i = 0; i < 29; i++) acc[i] = 0;
-
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-        const int j = seed[i];
-        if (j >= 0) {
-            const float4 p = __ldg(src + i);
-            const float3 q = xform_pt(T, p.x, p.y, p.z);
-            const float d2 = d2s[i];
-            icp_accumulate(acc, q, d2, __ldg(tgt + j), __ldg(nrm + j), scJJ, scJr, scd);
-        }
-    }
-    // block reduction (integer sums: any order gives the same bits)
-#pragma unroll
-    for (int i = 0; i < 29; i++) acc[i] = warp_sum_ll(acc[i]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 29; i++) red[warp][i] = acc[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < 29) {
-        long long s = 0;
-#pragma unroll
-        for (int w = 0; w < ICP_THREADS / 32; w++) s += red[w][threadIdx.x];
-        if (s != 0) atomicAdd((unsigned long long *)&S->acc[threadIdx.x], (unsigned long long)s);
-    }
-    __threadfence();
+// grid-wide barrier of a cooperative launch (all CTAs co-resident): monotonically increasing arrival counter
+__device__ __forceinline__ void icp_grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&S->ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        // release-arrive / acquire-poll (measured 20 % faster than fence + atomic + fence, tools/micro/barrier_bench.cu)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        while (ld_acquire_u32(bar) < target) {
+        }
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        icp_finish_pass(S, ns);
-    }
 }
 
-// correspondences from Morton order back to the caller's source order
-__global__ void __launch_bounds__(256) k_unpermute_corr(const float4 *__restrict__ src_sorted, const int *__restrict__ seed, int ns,
-                                                        int *__restrict__ corr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ns) corr[__float_as_int(__ldg(src_sorted + i).w)] = seed[i];
+// The WHOLE ICP loop in one persistent cooperative kernel (one launch per pcr_icp call, no host round trips).
+//
+// Per pass and source point (Morton order; a thread owns the same points in every pass, so seed[]/cert[] need no
+// inter-CTA coherence): transform by the cumulative fp64 transform (D7), nearest target point in the uniform grid
+// (certified reuse of the previous correspondence where provable, else the full search — identical results), then the
+// point-to-plane row (J, r) in fp64.  Per source point the state is seed[i] = current correspondence (-1: none) and
+// cert[i] = (query position at the last full search, lower bound of the squared distance to every OTHER target point):
+// if dist(q', t_j) + |q' - q_ref| is below that bound (triangle inequality, 2e-5 relative slack >> fp32 rounding),
+// j is still the unique nearest neighbour and d2 = fp32 dist2(q', t_j) is exactly what the search would return.
+//
+// Normal equations (rule D5): J (6 entries) and r are quantised ONCE per correspondence to kq-bit integers
+// (kq = min(30, (62 - ceil(log2 n)) / 2), scales 2^(kq - e_J), 2^(kq - e_R)); the 21 + 6 sums are sums of exact
+// int32 x int32 -> int64 products, so they are order-free and bit-reproducible, and one product costs ONE
+// IMAD.WIDE instead of DMUL + DMUL + F2I + 64-bit add.  The quantised rows of a 256-point chunk are staged in
+// shared memory (SoA, double-buffered, one __syncthreads per chunk) and the 27 products are split over the warps:
+// warp w forms the sums of entry group w & 3 (7 / 6 / 7 / 7 entries) for 4 rows per lane, so a thread carries
+// 7 accumulators (14 registers) instead of 27 (54) — the NN search keeps its occupancy.  The inlier count and
+// the fixed-point sum of d2 stay with the thread that owns the point.
+//
+// End of pass: one 64-bit atomic per CTA and sum into a triple-buffered accumulator, ONE grid barrier, then every
+// CTA solves the 6x6 system redundantly (bit-identical), so no second barrier / broadcast is needed.
+__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__restrict__ src, int ns, Grid g,
+                                                                const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
+                                                                float r2, IcpState *__restrict__ S, int *__restrict__ seed,
+                                                                float4 *__restrict__ cert, float2 *__restrict__ cert2, int *__restrict__ corr) {
+    __shared__ int rows[2][7][ICP_THREADS];
+    __shared__ long long red[ICP_WARPS][9];
+    __shared__ long long tot[29];
+    __shared__ double fA[6][6], fb[6];
+    __shared__ IcpLocal L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 16) L.T[threadIdx.x] = S->T[threadIdx.x];
+    if (threadIdx.x == 0) {
+        L.prev_fit = L.prev_rmse = L.fitness = L.rmse = 0.0;
+        L.count = L.sumq = 0;
+        L.pass = L.done = L.iterations = L.converged = 0;
+    }
+    const double scJ = S->sc_J, scR = S->sc_R, scd = S->sc_d;
+    const double isc_JJ = S->isc_JJ, isc_Jr = S->isc_Jr, isc_d = S->isc_d, rel_fit = S->rel_fit, rel_rmse = S->rel_rmse;
+    const int max_iter = S->max_iter;
+    const int dbgf = S->dbgflags;
+    const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
+    const int grp = warp & 3;                       // entry group of this warp
+    const int row0 = (warp >> 2) * (ICP_THREADS / 2) + lane;  // rows row0 + 32 k, k = 0..3
+    __syncthreads();
+
+    for (int pass = 0;; pass++) {
+        const double *T = L.T;  // broadcast shared-memory reads
+        long long acc[7];
+#pragma unroll
+        for (int e = 0; e < 7; e++) acc[e] = 0;
+        long long sumq = 0;
+        int cnt = 0, buf = 0;
+        const long long c0 = clock64();
+        for (int base = blockIdx.x * ICP_THREADS; base < ns; base += gridDim.x * ICP_THREADS, buf ^= 1) {
+            const int i = base + threadIdx.x;
+            int q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0, q6 = 0;
+            if (i < ns) {
+                const float4 p = __ldg(src + i);
+                const float3 q = (dbgf & 8) ? make_float3(p.x, p.y, p.z) : xform_pt(T, p.x, p.y, p.z);
+                float d2 = 0.0f;
+                const int j = (dbgf & 4) ? (i % g.n) : icp_point_nn(g, tgt, q, r2, max_dist_f, pass, i, seed, cert, cert2, &d2);
+                if (j >= 0 && !(dbgf & 2)) {
+                    const float4 tp = __ldg(tgt + j), np = __ldg(nrm + j);
+                    const double sx = q.x, sy = q.y, sz = q.z;
+                    const double nx = np.x, ny = np.y, nz = np.z;
+                    q0 = __double2int_rn(__dmul_rn(sy * nz - sz * ny, scJ));
+                    q1 = __double2int_rn(__dmul_rn(sz * nx - sx * nz, scJ));
+                    q2 = __double2int_rn(__dmul_rn(sx * ny - sy * nx, scJ));
+                    q3 = __double2int_rn(__dmul_rn(nx, scJ));
+                    q4 = __double2int_rn(__dmul_rn(ny, scJ));
+                    q5 = __double2int_rn(__dmul_rn(nz, scJ));
+                    q6 = __double2int_rn(__dmul_rn(((sx - (double)tp.x) * nx + (sy - (double)tp.y) * ny) + (sz - (double)tp.z) * nz, scR));
+                    cnt++;
+                    sumq += fixed_ll((double)d2, scd);
+                }
+            }
+            int(*rw)[ICP_THREADS] = rows[buf];
+            rw[0][threadIdx.x] = q0; rw[1][threadIdx.x] = q1; rw[2][threadIdx.x] = q2; rw[3][threadIdx.x] = q3;
+            rw[4][threadIdx.x] = q4; rw[5][threadIdx.x] = q5; rw[6][threadIdx.x] = q6;
+            __syncthreads();
+            if (!(dbgf & 1))
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = row0 + 32 * k;
+                const long long v3 = rw[3][r], v4 = rw[4][r], v5 = rw[5][r], v6 = rw[6][r];
+                if (grp == 0) {
+                    const long long v0 = rw[0][r], v1 = rw[1][r], v2 = rw[2][r];
+                    acc[0] += v0 * v0; acc[1] += v0 * v1; acc[2] += v0 * v2; acc[3] += v0 * v3;
+                    acc[4] += v0 * v4; acc[5] += v0 * v5; acc[6] += v0 * v6;
+                } else if (grp == 1) {
+                    const long long v1 = rw[1][r], v2 = rw[2][r];
+                    acc[0] += v1 * v1; acc[1] += v1 * v2; acc[2] += v1 * v3; acc[3] += v1 * v4;
+                    acc[4] += v1 * v5; acc[5] += v1 * v6;
+                } else if (grp == 2) {
+                    const long long v2 = rw[2][r];
+                    acc[0] += v2 * v2; acc[1] += v2 * v3; acc[2] += v2 * v4; acc[3] += v2 * v5;
+                    acc[4] += v2 * v6; acc[5] += v5 * v5; acc[6] += v5 * v6;
+                } else {
+                    acc[0] += v3 * v3; acc[1] += v3 * v4; acc[2] += v3 * v5; acc[3] += v3 * v6;
+                    acc[4] += v4 * v4; acc[5] += v4 * v5; acc[6] += v4 * v6;
+                }
+            }
+        }
+        // CTA reduction, then one atomic per sum and CTA into the pass's accumulator
+        long long *gacc = S->acc3[pass % 3];
+        const long long c1 = clock64();
+#pragma unroll
+        for (int e = 0; e < 7; e++) acc[e] = warp_sum_ll(acc[e]);
+        sumq = warp_sum_ll(sumq);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        __syncthreads();  // the accumulate phase of the last chunk is done in every warp before `red` is reused
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 7; e++) red[warp][e] = acc[e];
+            red[warp][7] = cnt;
+            red[warp][8] = sumq;
+        }
+        __syncthreads();
+        if (threadIdx.x < 29) {
+            // sum e lives in slot `sl` of the two warps of group `gr` (see the accumulate phase above)
+            const int e = threadIdx.x;
+            int gr, sl;
+            if (e < 6) { gr = 0; sl = e; }                       // (0,0..5)
+            else if (e < 11) { gr = 1; sl = e - 6; }             // (1,1..5)
+            else if (e < 15) { gr = 2; sl = e - 11; }            // (2,2..5)
+            else if (e < 18) { gr = 3; sl = e - 15; }            // (3,3..5)
+            else if (e < 20) { gr = 3; sl = e - 18 + 4; }        // (4,4), (4,5)
+            else if (e == 20) { gr = 2; sl = 5; }                // (5,5)
+            else if (e == 21) { gr = 0; sl = 6; }                // J0 r
+            else if (e == 22) { gr = 1; sl = 5; }                // J1 r
+            else if (e == 23) { gr = 2; sl = 4; }                // J2 r
+            else if (e == 24) { gr = 3; sl = 3; }                // J3 r
+            else if (e == 25) { gr = 3; sl = 6; }                // J4 r
+            else if (e == 26) { gr = 2; sl = 6; }                // J5 r
+            else { gr = -1; sl = e - 20; }                       // 27: count (slot 7), 28: sum d2 (slot 8), all warps
+            long long sum = 0;
+            if (gr >= 0) {
+                sum = red[gr][sl] + red[gr + 4][sl];
+            } else {
+#pragma unroll
+                for (int w = 0; w < ICP_WARPS; w++) sum += red[w][sl];
+            }
+            if (sum != 0) atomicAdd((unsigned long long *)&gacc[e], (unsigned long long)sum);
+        }
+        const long long cb = clock64();
+        if (threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgmax[pass], (unsigned long long)(c1 - c0));  // trace
+        icp_grid_barrier(&S->bar, (unsigned int)(pass + 1) * gridDim.x);
+        const long long ce = clock64();
+        if (threadIdx.x < 29) {
+            const long long v = __ldcg(&gacc[threadIdx.x]);
+            tot[threadIdx.x] = v;
+            const int e = threadIdx.x;
+            if (e < 21) {
+                int a = 0, rem = e;
+                while (rem >= 6 - a) { rem -= 6 - a; a++; }
+                const double d = (double)v * isc_JJ;
+                fA[a][a + rem] = d;
+                fA[a + rem][a] = d;
+            } else if (e < 27) {
+                fb[e - 21] = -((double)v * isc_Jr);
+            }
+        }
+        // the buffer of pass - 1 was read by every CTA before it arrived at this barrier; it is next used in pass + 2
+        if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 29) S->acc3[(pass + 2) % 3][threadIdx.x - 32] = 0;
+        __syncthreads();
+        const long long c2 = clock64();
+        if (threadIdx.x == 0) icp_finish_pass(&L, tot, fA, fb, isc_d, rel_fit, rel_rmse, max_iter, ns);
+        __syncthreads();
+        if (threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgfin[pass], (unsigned long long)(clock64() - c2));
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            S->dbg[0] += c1 - c0;
+            if (pass < 63) S->dbgp[pass] = c1 - c0;
+            S->dbg[1] += c2 - c1;
+            S->dbg[3] += ce - cb;
+            S->dbg[2] += clock64() - c2;
+        }
+        if (L.done) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 16; i++) S->T_out[i] = L.T[i];
+        S->fitness = L.fitness;
+        S->rmse = L.rmse;
+        S->count = L.count;
+        S->sumq = L.sumq;
+        S->pass = L.pass;
+        S->iterations = L.iterations;
+        S->converged = L.converged;
+        S->done = 1;
+    }
+    // Morton order back to the caller's source order (a thread reads only the seeds it wrote itself)
+    if (corr)
+        for (int base = blockIdx.x * ICP_THREADS; base < ns; base += gridDim.x * ICP_THREADS) {
+            const int i = base + threadIdx.x;
+            if (i < ns) corr[__float_as_int(__ldg(src + i).w)] = seed[i];
+        }
 }
 
 __global__ void __launch_bounds__(256) k_nn1(const float4 *__restrict__ q, int nq, Grid g, float r2,
@@ -337,38 +509,40 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     const int e_r = pcr_pow2ceil_exp(max_dist);
     const int e_J = pcr_pow2ceil_exp(2.0 * ((double)amax + max_dist) + 1.0);
     const int e_R = e_r + 2;
-    const int k_d = 62 - 2 * e_r - lg, k_JJ = 62 - 2 * e_J - lg, k_Jr = 62 - e_J - e_R - lg;
+    const int k_d = 62 - 2 * e_r - lg;
+    const int kq = (62 - lg) / 2 < 30 ? (62 - lg) / 2 : 30;  // bits per quantised factor
+    const int s_J = kq - e_J, s_R = kq - e_R;
 
     IcpState *hS = (IcpState *)ctx->pinned;
     memset(hS, 0, sizeof(IcpState));
     for (int i = 0; i < 16; i++) hS->T[i] = init[i];
     hS->max_iter = max_iter;
+    hS->dbgflags = getenv("PCR_ICP_DBG") ? atoi(getenv("PCR_ICP_DBG")) : 0;
     hS->rel_fit = rel_fit;
     hS->rel_rmse = rel_rmse;
-    hS->sc_JJ = ldexp(1.0, k_JJ); hS->isc_JJ = ldexp(1.0, -k_JJ);
-    hS->sc_Jr = ldexp(1.0, k_Jr); hS->isc_Jr = ldexp(1.0, -k_Jr);
+    hS->sc_J = ldexp(1.0, s_J); hS->isc_JJ = ldexp(1.0, -2 * s_J);
+    hS->sc_R = ldexp(1.0, s_R); hS->isc_Jr = ldexp(1.0, -(s_J + s_R));
     hS->sc_d = ldexp(1.0, k_d);   hS->isc_d = ldexp(1.0, -k_d);
     PCR_ALLOC(dS, IcpState, 1);
     PCR_ALLOC(seed, int, (size_t)ns);
-    PCR_ALLOC(d2s, float, (size_t)ns);
     PCR_ALLOC(cert, float4, (size_t)ns);
+    PCR_ALLOC(cert2, float2, (size_t)ns);
     PCR_CUDA(cudaMemsetAsync(seed, 0xff, sizeof(int) * (size_t)ns, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
-    const float r2 = (float)(max_dist * max_dist);
-    const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * 4);
-    const int nn_blocks = min(div_up(ns, 256), ctx->sm_count * 8);
+    float r2 = (float)(max_dist * max_dist);
+    // cooperative launch: every CTA must be resident (the kernel synchronises the grid once per pass)
+    static int occ = 0;
+    if (!occ) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp_persist, ICP_THREADS, 0));
+    if (occ < 1) return pcr_fail(ctx, PCR_ERR_CUDA, "k_icp_persist does not fit on an SM");
+    const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * occ);
     const size_t pend_idx = ctx->pending.size();
     {
+        // ONE launch runs all passes; the per-pass figure (52 B per point) is what the kernel statistics report,
+        // with the number of passes actually run filled in below
         KScope ks(ctx, KC_ICP_PASS, 16.0 * ns + 32.0 * nt + 4.0 * ns, max_iter + 1);
-        for (int pass = 0; pass <= max_iter; pass++) {
-            k_icp_nn<<<nn_blocks, 256, 0, ctx->stream>>>(src_sorted, ns, g, tgt, r2, dS, seed, d2s, cert);
-            PCR_LAUNCHED();
-            k_icp_accum<<<blocks, ICP_THREADS, 0, ctx->stream>>>(src_sorted, ns, tgt, nrm, dS, seed, d2s);
-            PCR_LAUNCHED();
-        }
-    }
-    if (corr) {
-        k_unpermute_corr<<<div_up(ns, 256), 256, 0, ctx->stream>>>(src_sorted, seed, ns, corr);
+        void *args[] = {(void *)&src_sorted, (void *)&ns, (void *)&g, (void *)&tgt, (void *)&nrm, (void *)&r2, (void *)&dS,
+                        (void *)&seed, (void *)&cert, (void *)&cert2, (void *)&corr};
+        PCR_CUDA(cudaLaunchCooperativeKernel((const void *)k_icp_persist, dim3(blocks), dim3(ICP_THREADS), args, 0, ctx->stream));
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
@@ -383,6 +557,18 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
         res->k_d = k_d;
         res->iterations = hS->iterations;
         res->converged = hS->converged;
+        if (getenv("PCR_ICP_TRACE"))
+            fprintf(stderr, "[pcr icp] ns %d passes %d blocks %d cycles/pass: loop %.0f  reduce+barrier %.0f  finish %.0f\n", ns, hS->pass,
+                    blocks, (double)hS->dbg[0] / hS->pass, (double)hS->dbg[1] / hS->pass, (double)hS->dbg[2] / hS->pass);
+        if (getenv("PCR_ICP_TRACE")) {
+            fprintf(stderr, "[pcr icp] loop cycles per pass:");
+            for (int i = 0; i < hS->pass && i < 12; i++) fprintf(stderr, " %lld", hS->dbgp[i]);
+            fprintf(stderr, "\n[pcr icp] slowest CTA loop per pass:");
+            for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgmax[i]);
+            fprintf(stderr, "\n[pcr icp] slowest CTA finish per pass:");
+            for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgfin[i]);
+            fprintf(stderr, "  barrier alone %.0f\n", (double)hS->dbg[3] / hS->pass);
+        }
         // passes that did work (the rest returned at the `done` check): iterations + 1
         if (ctx->profiling && pend_idx < ctx->pending.size()) ctx->pending[pend_idx].launches = hS->pass;
     }

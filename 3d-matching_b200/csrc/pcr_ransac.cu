@@ -219,13 +219,18 @@ __global__ void __launch_bounds__(128) k_ransac_generate(const float4 *__restric
     for (int k = 0; k < 12; k++) surv[slot].T[k] = T[k];
 }
 
-constexpr int VAL_THREADS = 256;
-
+// VAL_THREADS = 256 for pruned waves (many survivors, most of them rejected after a few chunks), 1024 for the first
+// ("blind") wave, where nothing can be pruned yet and the latency of one full evaluation is what matters.
+// The 256-point chunks of the Morton-ordered source are visited in a strided order (stride coprime with the number
+// of chunks), so that the first few chunks already sample the whole cloud: the misses of a slightly-off hypothesis,
+// which cluster at the far ends of the object, are seen early and the exact pruning rule fires after a few chunks
+// instead of most of them.  The pruning rule itself does not depend on the order.
+template <int VAL_THREADS>
 __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g, const int2 *__restrict__ corr, int c,
     double max_dist, float r2, double sc_d, const Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
     long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs, unsigned int *__restrict__ n_recs,
-    unsigned int rec_cap) {
+    unsigned int rec_cap, int chunk_stride) {
     __shared__ double sT[12];
     __shared__ long long red[VAL_THREADS / 32][3];
     const unsigned int ns = *n_surv;
@@ -244,7 +249,13 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
         int found = 0;
         long long partial = 0;
         bool pruned = false;
-        for (int base = 0; base < ms; base += VAL_THREADS) {
+        const int nchunks = (ms + VAL_THREADS - 1) / VAL_THREADS;
+        int done_pts = 0, chunk = 0;
+        for (int kc = 0; kc < nchunks; kc++) {
+            const int base = chunk * VAL_THREADS;
+            chunk += chunk_stride;
+            if (chunk >= nchunks) chunk -= nchunks;
+            done_pts += min(VAL_THREADS, ms - base);
             const int i = base + threadIdx.x;
             bool hit = false;
             long long q_add = 0;
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
                 }
             }
             found += __syncthreads_count(hit);
-            const int remaining = ms - min(ms, base + VAL_THREADS);
+            const int remaining = ms - done_pts;
             if ((long long)found + remaining < best_cnt) {
                 pruned = true;
                 break;
@@ -429,14 +440,25 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
                                                                        hyp_begin, count, seed, surv, counters);
         PCR_LAUNCHED();
     }
-    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * 8);
+    const bool blind = best_cnt <= 0;  // nothing to prune against yet: few survivors, full evaluations
+    const int vthreads = blind ? 1024 : 256;
+    const int nchunks = div_up(ms, vthreads);
+    int stride = (int)(nchunks * 0.618);  // stride coprime with the chunk count (1 when there are < 3 chunks)
+    if (stride < 1) stride = 1;
+    while (stride > 1 && std::__gcd(stride, nchunks) != 1) stride--;
+    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * (blind ? 1 : 8));
     const size_t pend_idx = ctx->pending.size();
     {
-    KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
-    k_ransac_validate<<<vblocks, VAL_THREADS, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
-                                                                w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt,
-                                                                best_sumq, recs, counters + 1, (unsigned int)cap);
-    PCR_LAUNCHED();
+        KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
+        if (blind)
+            k_ransac_validate<1024><<<vblocks, 1024, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
+                                                                        w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
+                                                                        recs, counters + 1, (unsigned int)cap, stride);
+        else
+            k_ransac_validate<256><<<vblocks, 256, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
+                                                                      w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
+                                                                      recs, counters + 1, (unsigned int)cap, stride);
+        PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
     unsigned char *hp = (unsigned char *)ctx->pinned;
@@ -524,7 +546,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
     std::vector<pcr_hyp_record> recs;
-    int64_t begin = 0, wave = 8192;  // first wave small enough for the common early exit, then x4 to fill the GPU
+    int64_t begin = 0, wave = 2048;  // small blind first wave (no best to prune against yet), then x4 to fill the GPU
     int64_t survivors = 0;
     while (begin < max_iter && begin < res->est_k) {
         const int64_t end = std::min<int64_t>(max_iter, begin + wave);

@@ -1090,7 +1090,10 @@ ORC_API int orc_icp_point_to_plane(const float *src, int ns, const float *tgt, c
     const int e_r = pow2ceil_exp(max_dist);
     const int e_J = pow2ceil_exp(2.0 * ((double)amax + max_dist) + 1.0);
     const int e_R = e_r + 2;
-    const int k_d = 62 - 2 * e_r - lg, k_JJ = 62 - 2 * e_J - lg, k_Jr = 62 - e_J - e_R - lg;
+    const int k_d = 62 - 2 * e_r - lg;
+    /* D5 (ICP): J and r are quantised once per correspondence to kq-bit integers; the sums are exact integer products */
+    const int kq = (62 - lg) / 2 < 30 ? (62 - lg) / 2 : 30;
+    const int s_J = kq - e_J, s_R = kq - e_R;
     res->k_d = k_d;
     double T[16];
     memcpy(T, T_init, sizeof(T));
@@ -1119,10 +1122,13 @@ ORC_API int orc_icp_point_to_plane(const float *src, int ns, const float *tgt, c
                 const double nx = np[0], ny = np[1], nz = np[2];
                 const double r = (((sx - (double)tp[0]) * nx + (sy - (double)tp[1]) * ny)) + (sz - (double)tp[2]) * nz;
                 const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+                long long qJ[6];
+                for (int a = 0; a < 6; a++) qJ[a] = llrint(ldexp(J[a], s_J));
+                const long long qr = llrint(ldexp(r, s_R));
                 int e = 0;
                 for (int a = 0; a < 6; a++)
-                    for (int c = a; c < 6; c++) A->JJ[e++] += llrint(ldexp(J[a] * J[c], k_JJ));
-                for (int a = 0; a < 6; a++) A->Jr[a] += llrint(ldexp(J[a] * r, k_Jr));
+                    for (int c = a; c < 6; c++) A->JJ[e++] += qJ[a] * qJ[c];
+                for (int a = 0; a < 6; a++) A->Jr[a] += qJ[a] * qr;
                 A->cnt++;
                 A->sumq += llrint(ldexp((double)b.d2, k_d));
             }
@@ -1153,8 +1159,8 @@ ORC_API int orc_icp_point_to_plane(const float *src, int ns, const float *tgt, c
             double Am[6][6], bv[6], x[6];
             int e = 0;
             for (int a = 0; a < 6; a++)
-                for (int c = a; c < 6; c++) { Am[a][c] = Am[c][a] = ldexp((double)S.JJ[e], -k_JJ); e++; }
-            for (int a = 0; a < 6; a++) bv[a] = -ldexp((double)S.Jr[a], -k_Jr);
+                for (int c = a; c < 6; c++) { Am[a][c] = Am[c][a] = ldexp((double)S.JJ[e], -2 * s_J); e++; }
+            for (int a = 0; a < 6; a++) bv[a] = -ldexp((double)S.Jr[a], -(s_J + s_R));
             if (ldlt6_solve(Am, bv, x) == 0) vec6_to_mat4(x, U);
         }
         double Tn[16];

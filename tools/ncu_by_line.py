@@ -33,7 +33,12 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-s
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r)
 h = rows[hi]
-body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+body = []
+for r in rows[hi + 1:]:
+    if r == h:  # ncu prints the view twice
+        break
+    if len(r) == len(h):
+        body.append(r)
 ie, ss = h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
 f = lambda x: float(x) if x.replace(".", "", 1).isdigit() else 0.0
 print(f"sass lines: ncu {len(body)} nvdisasm {len(lines_of) if lines_of else None}")
@@ -43,7 +48,8 @@ for i, r in enumerate(body):
     agg[key][0] += f(r[ie]); agg[key][1] += f(r[ss])
 ti = sum(v[0] for v in agg.values()) or 1; ts = sum(v[1] for v in agg.values()) or 1
 srcs = {}
-for (fn, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+by = 1 if (len(sys.argv) > 5 and sys.argv[5] == "stall") else 0
+for (fn, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][by])[:topn]:
     path = os.path.join(os.path.dirname(SO), "..", "csrc", fn) if fn else None
     text = ""
     try:

@@ -16,5 +16,5 @@ if os.environ.get("ICP1M", "1") == "1":
     s1, t1, _ = synth.make_icp_pair(1000000, v, 20243)
     d1s, d1t = eng.pack(s1), eng.pack(t1)
     nrm = eng.estimate_normals(d1t, 2 * v, 30)
-    g, _ = eng.icp_point_to_plane(d1s, d1t, nrm, 0.4 * v, np.eye(4), 3, 0.0, 0.0)
+    g, _ = eng.icp_point_to_plane(d1s, d1t, nrm, 0.4 * v, np.eye(4), int(os.environ.get("ICP1M_ITERS", "3")), 0.0, 0.0)
     print("icp1m ok", g.fitness)
