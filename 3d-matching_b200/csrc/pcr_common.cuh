@@ -115,6 +115,7 @@ struct Grid {
     double h;
     int nx, ny, nz;
     int n;
+    int R;                  // rings of cells that cover the search radius (1 unless built by pcr_grid_build_rings)
 };
 
 // bounds: lo/hi (host) of a float4 cloud; one device reduction + one D2H sync
@@ -122,6 +123,10 @@ int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3])
 // build a search grid supporting radius-`radius` queries with a 3x3x3 cell probe.
 // If bounds are already known pass them (have_bounds), else they are computed.
 int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo, const float *hi, Grid *g);
+// same, with cells of size radius / rings (rings = 1 or 2): a radius query then probes a (2 R + 1)^3 block, R = g->R.
+// Finer cells pay off for k-nearest queries on dense clouds, where the k-th neighbour is much closer than the radius.
+int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, int rings, const float *lo, const float *hi,
+                         Grid *g);
 // Morton-order copy of a cloud (dense counting sort on interleaved cell ids; .w = original index): consecutive
 // points are spatially compact, which the warp-cooperative joins rely on
 int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out);

@@ -239,7 +239,13 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const float4 *__restrict__
 
 int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo_in, const float *hi_in,
                    Grid *g) {
-    if (n <= 0 || !(radius > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: n=%d radius=%g", n, radius);
+    return pcr_grid_build_rings(ctx, pts, n, radius, 1, lo_in, hi_in, g);
+}
+
+int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, int rings, const float *lo_in,
+                         const float *hi_in, Grid *g) {
+    if (n <= 0 || !(radius > 0.0) || rings < 1 || rings > 2)
+        return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: n=%d radius=%g rings=%d", n, radius, rings);
     float lo[3], hi[3];
     if (lo_in && hi_in) {
         for (int d = 0; d < 3; d++) { lo[d] = lo_in[d]; hi[d] = hi_in[d]; }
@@ -250,7 +256,8 @@ int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const 
         if (!(lo[d] <= hi[d]) || isinf(lo[d]) || isinf(hi[d]))
             return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: non-finite coordinates");
     // cell size: radius with a 2^-10 margin, enlarged (x1.25 steps) until the dense table fits the budget
-    double h = radius * (1.0 + 1.0 / 1024.0);
+    const double reach = radius * (1.0 + 1.0 / 1024.0);
+    double h = reach / rings;
     long long nx, ny, nz;
     for (;;) {
         nx = (long long)floor(((double)hi[0] - (double)lo[0]) / h) + 1;
@@ -281,6 +288,8 @@ int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const 
     g->h = h;
     g->nx = gd.nx; g->ny = gd.ny; g->nz = gd.nz;
     g->n = n;
+    g->R = 1;
+    while ((double)g->R * h < reach) g->R++;  // R h >= radius (1 + 2^-10): the block covers the radius with the margin
     return PCR_OK;
 }
 

@@ -21,7 +21,6 @@ struct IcpState {
     double T[16];
     long long acc3[3][32];  // triple-buffered: 0..20 JtJ upper triangle (row-major), 21..26 Jtr, 27 count, 28 sum d2
     unsigned int bar;       // grid-barrier arrival counter
-    int dbgflags;           // PCR_ICP_DBG (development only): 1 skip accumulate, 2 skip rows, 4 skip NN, 8 skip xform
     int pass;
     int done;
     int iterations;
@@ -149,40 +148,55 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
 constexpr int ICP_THREADS = 256;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 
-// Correspondence of one transformed source point q (index i in Morton order): certified reuse or full search; keeps
-// seed[i] / cert[i] up to date (see k_icp_persist).  Returns the target index or -1 and the fp32 squared distance.
+// Result of the correspondence step for one source point: target index (-1: none), fp32 squared distance, and the
+// matched target point and normal.
+struct IcpMatch {
+    int j;
+    float d2;
+    float tx, ty, tz, nx, ny, nz;
+};
+
+// Correspondence of one transformed source point q (index i in Morton order): certified reuse or full search.
 //
-// cert[i] = (q_ref, w): q_ref is the query position at the last certificate search (grid_nn1_cert, which examines
-// every target point within one cell size h > max_dist of q_ref).
-//   w > 0 : a correspondence j existed; w is a lower bound of the squared distance from q_ref to every OTHER target
+// Per-point state (written and read only by the thread that owns the point, see k_icp_persist), denormalised so that
+// a certified pass is pure streaming — four coalesced 16-byte loads, no dependent gather:
+//   st0[i] = (q_ref, w)   query position at the last certificate search (grid_nn1_cert, which examines every target
+//                         point within one cell size h > max_dist of q_ref) and the certificate w (below)
+//   st1[i] = (t_j, j)     current correspondence: target point and index (index -1: none)
+//   st2[i] = (n_j, -)     its normal
+//   cert2[i] = (j2, w3)   second tier (below)
+//   w > 0 : a correspondence j exists; w is a lower bound of the squared distance from q_ref to every OTHER target
 //           point.  For the new position q, with delta = |q - q_ref|: every other point is at least sqrt(w) - delta
 //           away, so if dist(q, t_j) < sqrt(w) - delta then j is still the unique nearest point, and
 //           d2 = fp32 dist2(q, t_j) is exactly what the search would return (the radius rule is re-applied).
 //   w < 0 : no correspondence; -w is a lower bound of the squared distance from q_ref to EVERY target point, so if
 //           sqrt(-w) - delta > max_dist there is still none.
-//   w = 0 : no certificate (passes 0..1 use the cheaper pruned search while the cloud still moves).
 // Near-ties (second nearest almost as close as the nearest: a fraction ~1e-4 of the points, and persistently so once
-// the cloud has stopped moving) would fail that test in every pass, and one such point stalls its whole CTA in a full
-// search.  They take a second tier: cert2[i] = (j2, w3) holds the second nearest point and a lower bound for every
-// point other than the nearest two; j is kept if it beats j2 in the exact (d2, index) key order and beats w3 as above.
+// the cloud has stopped moving — some even flip back and forth under the last-bit jitter of the converged transform)
+// would fail that test in every pass, and one such point stalls its whole CTA in a full search.  They take a second
+// tier: cert2[i] = (j2, w3) holds the second nearest point and a lower bound for every point other than the nearest
+// two; the winner of the exact (d2, index) key comparison between j and j2 is kept if it beats w3 as above.
+// Passes 0..1 use the cheaper pruned search while the cloud still moves (no certificate is read before pass 3).
 // All bound comparisons carry a 2e-5 relative slack on both sides, orders of magnitude above the fp32 rounding of
 // the distances involved, so a certified answer is always the exact answer.
-__device__ __forceinline__ int icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, float3 q, float r2, float max_dist_f, int pass,
-                                            int i, int *__restrict__ seed, float4 *__restrict__ cert, float2 *__restrict__ cert2,
-                                            float *d2_out) {
+__device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, const float4 *__restrict__ nrm, float3 q,
+                                             float r2, float max_dist_f, int pass, int i, float4 *__restrict__ st0,
+                                             float4 *__restrict__ st1, float4 *__restrict__ st2, float2 *__restrict__ cert2,
+                                             IcpMatch &o) {
     if (pass >= 3) {
-        const float4 c = cert[i];
+        const float4 c = st0[i], a = st1[i], b = st2[i];
         const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
         const float delta = sqrtf((mx * mx + my * my) + mz * mz);
         if (c.w > 0.0f) {
-            const int j_old = seed[i];
-            const float4 t = __ldg(tgt + j_old);
-            const float d1 = dist2f(q.x, q.y, q.z, t.x, t.y, t.z);
+            const int j_old = __float_as_int(a.w);
+            const float d1 = dist2f(q.x, q.y, q.z, a.x, a.y, a.z);
+            o.tx = a.x; o.ty = a.y; o.tz = a.z; o.nx = b.x; o.ny = b.y; o.nz = b.z;
             // (a certified nearest point that has drifted out of the radius takes the search path, which then
             // records a "no correspondence" certificate)
             if (d1 < r2 && (sqrtf(d1) + delta) * 1.00002f < sqrtf(c.w) * 0.99998f) {
-                *d2_out = d1;
-                return j_old;
+                o.j = j_old;
+                o.d2 = d1;
+                return;
             }
             const float2 c2 = cert2[i];
             const int j2 = __float_as_int(c2.x);
@@ -196,45 +210,48 @@ __device__ __forceinline__ int icp_point_nn(const Grid &g, const float4 *__restr
                 const float dw = a_wins ? d1 : d2b;
                 if (dw < r2 && (sqrtf(dw) + delta) * 1.00002f < sqrtf(c2.y) * 0.99998f) {
                     if (!a_wins) {
-                        // the pair swaps roles (a correspondence that flips under the last-bit jitter of a
-                        // converged transform): w no longer bounds "all points but the nearest", so it is set to
-                        // a value that always defers to this tier; w3 bounds every point outside the pair as before
-                        seed[i] = j2;
+                        // the pair swaps roles: w no longer bounds "all points but the nearest", so it is set to a
+                        // value that always defers to this tier; w3 bounds every point outside the pair as before
+                        const float4 n2 = __ldg(nrm + j2);
+                        st0[i] = make_float4(c.x, c.y, c.z, 1.17549435e-38f);
+                        st1[i] = make_float4(t2.x, t2.y, t2.z, __int_as_float(j2));
+                        st2[i] = n2;
                         cert2[i] = make_float2(__int_as_float(j_old), c2.y);
-                        cert[i] = make_float4(c.x, c.y, c.z, 1.17549435e-38f);
+                        o.tx = t2.x; o.ty = t2.y; o.tz = t2.z; o.nx = n2.x; o.ny = n2.y; o.nz = n2.z;
                     }
-                    *d2_out = dw;
-                    return a_wins ? j_old : j2;
+                    o.j = a_wins ? j_old : j2;
+                    o.d2 = dw;
+                    return;
                 }
             }
         } else if (c.w < 0.0f) {
             if ((max_dist_f + delta) * 1.00002f < sqrtf(-c.w) * 0.99998f) {
-                *d2_out = 0.0f;
-                return -1;
+                o.j = -1;
+                o.d2 = 0.0f;
+                return;
             }
         }
     }
-    float d2;
-    int j;
-    if (pass >= 2) {
-        float other, third;
-        int j2;
-        j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
-        if (j >= 0) {
-            seed[i] = j;
-            cert[i] = make_float4(q.x, q.y, q.z, other);
+    float d2, other = 0.0f, third = 0.0f;
+    int j, j2 = -1;
+    if (pass >= 2) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
+    else j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
+    o.j = j;
+    o.d2 = d2;
+    if (j >= 0) {
+        const float4 tp = __ldg(tgt + j), np = __ldg(nrm + j);
+        o.tx = tp.x; o.ty = tp.y; o.tz = tp.z; o.nx = np.x; o.ny = np.y; o.nz = np.z;
+        st1[i] = make_float4(tp.x, tp.y, tp.z, __int_as_float(j));
+        if (pass >= 2) {
+            st0[i] = make_float4(q.x, q.y, q.z, other);
+            st2[i] = np;
             cert2[i] = make_float2(__int_as_float(j2), third);
-        } else {
-            seed[i] = -1;
-            // nothing inside the radius: every target point is at least min(nearest examined, h) away
-            cert[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
         }
     } else {
-        j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
-        seed[i] = j;
+        st1[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+        // nothing inside the radius: every target point is at least min(nearest examined, h) away
+        if (pass >= 2) st0[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
     }
-    *d2_out = d2;
-    return j;
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -278,8 +295,9 @@ __device__ __forceinline__ void icp_grid_barrier(unsigned int *bar, unsigned int
 // CTA solves the 6x6 system redundantly (bit-identical), so no second barrier / broadcast is needed.
 __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__restrict__ src, int ns, Grid g,
                                                                 const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
-                                                                float r2, IcpState *__restrict__ S, int *__restrict__ seed,
-                                                                float4 *__restrict__ cert, float2 *__restrict__ cert2, int *__restrict__ corr) {
+                                                                float r2, IcpState *__restrict__ S, float4 *__restrict__ st0,
+                                                                float4 *__restrict__ st1, float4 *__restrict__ st2,
+                                                                float2 *__restrict__ cert2, int *__restrict__ corr) {
     __shared__ int rows[2][7][ICP_THREADS];
     __shared__ long long red[ICP_WARPS][9];
     __shared__ long long tot[29];
@@ -295,7 +313,6 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__
     const double scJ = S->sc_J, scR = S->sc_R, scd = S->sc_d;
     const double isc_JJ = S->isc_JJ, isc_Jr = S->isc_Jr, isc_d = S->isc_d, rel_fit = S->rel_fit, rel_rmse = S->rel_rmse;
     const int max_iter = S->max_iter;
-    const int dbgf = S->dbgflags;
     const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
     const int grp = warp & 3;                       // entry group of this warp
     const int row0 = (warp >> 2) * (ICP_THREADS / 2) + lane;  // rows row0 + 32 k, k = 0..3
@@ -314,29 +331,27 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__
             int q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0, q6 = 0;
             if (i < ns) {
                 const float4 p = __ldg(src + i);
-                const float3 q = (dbgf & 8) ? make_float3(p.x, p.y, p.z) : xform_pt(T, p.x, p.y, p.z);
-                float d2 = 0.0f;
-                const int j = (dbgf & 4) ? (i % g.n) : icp_point_nn(g, tgt, q, r2, max_dist_f, pass, i, seed, cert, cert2, &d2);
-                if (j >= 0 && !(dbgf & 2)) {
-                    const float4 tp = __ldg(tgt + j), np = __ldg(nrm + j);
+                const float3 q = xform_pt(T, p.x, p.y, p.z);
+                IcpMatch m;
+                icp_point_nn(g, tgt, nrm, q, r2, max_dist_f, pass, i, st0, st1, st2, cert2, m);
+                if (m.j >= 0) {
                     const double sx = q.x, sy = q.y, sz = q.z;
-                    const double nx = np.x, ny = np.y, nz = np.z;
+                    const double nx = m.nx, ny = m.ny, nz = m.nz;
                     q0 = __double2int_rn(__dmul_rn(sy * nz - sz * ny, scJ));
                     q1 = __double2int_rn(__dmul_rn(sz * nx - sx * nz, scJ));
                     q2 = __double2int_rn(__dmul_rn(sx * ny - sy * nx, scJ));
                     q3 = __double2int_rn(__dmul_rn(nx, scJ));
                     q4 = __double2int_rn(__dmul_rn(ny, scJ));
                     q5 = __double2int_rn(__dmul_rn(nz, scJ));
-                    q6 = __double2int_rn(__dmul_rn(((sx - (double)tp.x) * nx + (sy - (double)tp.y) * ny) + (sz - (double)tp.z) * nz, scR));
+                    q6 = __double2int_rn(__dmul_rn(((sx - (double)m.tx) * nx + (sy - (double)m.ty) * ny) + (sz - (double)m.tz) * nz, scR));
                     cnt++;
-                    sumq += fixed_ll((double)d2, scd);
+                    sumq += fixed_ll((double)m.d2, scd);
                 }
             }
             int(*rw)[ICP_THREADS] = rows[buf];
             rw[0][threadIdx.x] = q0; rw[1][threadIdx.x] = q1; rw[2][threadIdx.x] = q2; rw[3][threadIdx.x] = q3;
             rw[4][threadIdx.x] = q4; rw[5][threadIdx.x] = q5; rw[6][threadIdx.x] = q6;
             __syncthreads();
-            if (!(dbgf & 1))
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int r = row0 + 32 * k;
@@ -449,7 +464,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__
     if (corr)
         for (int base = blockIdx.x * ICP_THREADS; base < ns; base += gridDim.x * ICP_THREADS) {
             const int i = base + threadIdx.x;
-            if (i < ns) corr[__float_as_int(__ldg(src + i).w)] = seed[i];
+            if (i < ns) corr[__float_as_int(__ldg(src + i).w)] = __float_as_int(st1[i].w);
         }
 }
 
@@ -517,17 +532,16 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     memset(hS, 0, sizeof(IcpState));
     for (int i = 0; i < 16; i++) hS->T[i] = init[i];
     hS->max_iter = max_iter;
-    hS->dbgflags = getenv("PCR_ICP_DBG") ? atoi(getenv("PCR_ICP_DBG")) : 0;
     hS->rel_fit = rel_fit;
     hS->rel_rmse = rel_rmse;
     hS->sc_J = ldexp(1.0, s_J); hS->isc_JJ = ldexp(1.0, -2 * s_J);
     hS->sc_R = ldexp(1.0, s_R); hS->isc_Jr = ldexp(1.0, -(s_J + s_R));
     hS->sc_d = ldexp(1.0, k_d);   hS->isc_d = ldexp(1.0, -k_d);
     PCR_ALLOC(dS, IcpState, 1);
-    PCR_ALLOC(seed, int, (size_t)ns);
-    PCR_ALLOC(cert, float4, (size_t)ns);
+    PCR_ALLOC(st0, float4, (size_t)ns);
+    PCR_ALLOC(st1, float4, (size_t)ns);
+    PCR_ALLOC(st2, float4, (size_t)ns);
     PCR_ALLOC(cert2, float2, (size_t)ns);
-    PCR_CUDA(cudaMemsetAsync(seed, 0xff, sizeof(int) * (size_t)ns, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     float r2 = (float)(max_dist * max_dist);
     // cooperative launch: every CTA must be resident (the kernel synchronises the grid once per pass)
@@ -541,7 +555,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
         // with the number of passes actually run filled in below
         KScope ks(ctx, KC_ICP_PASS, 16.0 * ns + 32.0 * nt + 4.0 * ns, max_iter + 1);
         void *args[] = {(void *)&src_sorted, (void *)&ns, (void *)&g, (void *)&tgt, (void *)&nrm, (void *)&r2, (void *)&dS,
-                        (void *)&seed, (void *)&cert, (void *)&cert2, (void *)&corr};
+                        (void *)&st0, (void *)&st1, (void *)&st2, (void *)&cert2, (void *)&corr};
         PCR_CUDA(cudaLaunchCooperativeKernel((const void *)k_icp_persist, dim3(blocks), dim3(ICP_THREADS), args, 0, ctx->stream));
         PCR_LAUNCHED();
     }

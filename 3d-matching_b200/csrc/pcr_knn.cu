@@ -10,6 +10,8 @@
 // appended to a per-warp shared-memory buffer as 64-bit keys (fp32 d2 bits << 32 | index): key order IS the
 // (d2, index) order of determinism rule D2.  A warp-wide bitonic sort of the buffer yields the neighbour
 // list; when the buffer fills it is sorted and truncated to max_nn and the admission threshold tightens.
+#include <cstdlib>
+
 #include "pcr_common.cuh"
 
 constexpr int KNN_WARPS = 4;
@@ -123,38 +125,53 @@ __device__ __forceinline__ u64 warp_bitonic_merge32(u64 v, int lane) {  // v bit
     return v;
 }
 
-// returns the number of neighbours (<= max_nn <= 32); *best_out = this lane's key of the ascending list
+// (dy, dz) offsets of the rows of a (2R+1)^2 block, nearest rows first; the first 9 entries are the R = 1 block
+__constant__ signed char KNN_ROW_DY[25] = {0, -1, 1, 0, 0, -1, -1, 1, 1, -2, 2, 0, 0, -2, -2, 2, 2, -1, 1, -1, 1, -2, -2, 2, 2};
+__constant__ signed char KNN_ROW_DZ[25] = {0, 0, 0, -1, 1, -1, 1, -1, 1, 0, 0, -2, 2, -1, 1, -1, 1, -2, -2, 2, 2, -2, 2, -2, 2};
+
+// returns the number of neighbours (<= max_nn <= 32); *best_out = this lane's key of the ascending list.
+// The grid may have cells finer than the radius (g.R = 1 or 2 rings): rows are visited nearest first, a row whose slab
+// is provably farther than the current admission threshold (radius, then the max_nn-th distance) is skipped, and so
+// are the cells of a row beyond that distance in x (both bounds carry a 1e-4-cell slack that dominates the fp32
+// rounding involved; cells at exactly the threshold distance are kept).  On a dense cloud the list fills up in the
+// first few rows of fine cells and most of the block is never touched; the result does not depend on R.
 __device__ __forceinline__ int warp_knn_top32(const Grid &g, float qx, float qy, float qz, float r2, int max_nn, int lane,
                                               u64 *best_out) {
     const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
-    const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
-    const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
-    const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
+    const int R = g.R;
+    const int cx = (int)fmin(fmax(floor(fx), -1.0 - R), (double)g.nx + R);
+    const int cy = (int)fmin(fmax(floor(fy), -1.0 - R), (double)g.ny + R);
+    const int cz = (int)fmin(fmax(floor(fz), -1.0 - R), (double)g.nz + R);
     const u64 INF = ~0ull;
     u64 best = INF;
     u64 thr = ((u64)__float_as_uint(r2)) << 32;  // admissible: key < thr
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
     if (x0 <= x1) {
-        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-        const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
-        const float h2 = (float)(g.h * g.h);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
+        const float fxf = (float)fmin(fmax(fx, -4.0 - R), (double)g.nx + 4.0 + R);
+        const float fyf = (float)fmin(fmax(fy, -4.0 - R), (double)g.ny + 4.0 + R), fzf = (float)fmin(fmax(fz, -4.0 - R), (double)g.nz + 4.0 + R);
+        const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
+        const int nrows = (2 * R + 1) * (2 * R + 1);
 #pragma unroll 1
-        for (int o = 0; o < 9; o++) {
-            const int dy = (o == 0) ? 0 : ((o - 1) < 3 ? -1 : ((o - 1) < 5 ? 0 : 1));
-            const int dz = (o == 0) ? 0 : ((o - 1) < 3 ? (o - 2) : ((o - 1) < 5 ? ((o - 1) == 3 ? -1 : 1) : (o - 7)));
-            const int y = cy + dy, z = cz + dz;
+        for (int o = 0; o < nrows; o++) {
+            const int y = cy + KNN_ROW_DY[o], z = cz + KNN_ROW_DZ[o];
             if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+            const float tdist2 = __uint_as_float((uint32_t)(thr >> 32));
             if (o > 0) {
                 const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
                 const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
                 const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
                 // skip only if strictly farther than the admission threshold's distance (ties are kept)
-                if ((sy * sy + sz * sz) * h2 > __uint_as_float((uint32_t)(thr >> 32))) continue;
+                if ((sy * sy + sz * sz) * h2 > tdist2) continue;
             }
+            // cells of the row that can hold an admissible point (in cell units, padded)
+            const float rc = sqrtf(tdist2) * inv_hf * 1.0001f + 1e-4f;
+            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
+            if (xa > xb) continue;
             const long long row = ((long long)z * g.ny + y) * g.nx;
-            const uint32_t b = __ldg(g.start + row + x0);
-            const uint32_t e = __ldg(g.start + row + x1 + 1);
+            const uint32_t b = __ldg(g.start + row + xa);
+            const uint32_t e = __ldg(g.start + row + xb + 1);
             for (uint32_t base = b; base < e; base += 32) {
                 const uint32_t k = base + lane;
                 u64 key = INF;
@@ -557,7 +574,10 @@ int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int 
         return pcr_fail(ctx, PCR_ERR_INVALID, "normals: radius must be > 0 and 1 <= max_nn <= %d", KNN_CAP / 2);
     if (n == 0) return PCR_OK;
     Grid g;
-    PCR_TRY(pcr_grid_build(ctx, pts, n, radius, nullptr, nullptr, &g));
+    // The register top-32 search also handles finer cells (2 rings); measured on the 100k-point cloud that is SLOWER
+    // (0.97 vs 0.83 ms per alignment: more, shorter rows — the per-row latency dominates), so 1 ring is the default.
+    static const int rings = getenv("PCR_KNN_RINGS") ? atoi(getenv("PCR_KNN_RINGS")) : 1;
+    PCR_TRY(pcr_grid_build_rings(ctx, pts, n, radius, (max_nn <= 32 && rings == 2) ? 2 : 1, nullptr, nullptr, &g));
     PCR_ALLOC(cov, double, (size_t)n * 6);
     {
         KScope ks(ctx, KC_KNN_COV, 32.0 * n + 48.0 * n);

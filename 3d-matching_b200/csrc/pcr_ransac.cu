@@ -230,12 +230,18 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g, const int2 *__restrict__ corr, int c,
     double max_dist, float r2, double sc_d, const Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
     long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs, unsigned int *__restrict__ n_recs,
-    unsigned int rec_cap, int chunk_stride) {
+    unsigned int rec_cap, int chunk_stride, unsigned int *__restrict__ next_surv) {
     __shared__ double sT[12];
     __shared__ long long red[VAL_THREADS / 32][3];
+    __shared__ unsigned int s_next;
     const unsigned int ns = *n_surv;
-    for (unsigned int sidx = blockIdx.x; sidx < ns; sidx += gridDim.x) {
+    // survivors are handed out dynamically: evaluations range from one chunk (pruned) to the whole cloud
+    for (;;) {
         __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(next_surv, 1u);
+        __syncthreads();
+        const unsigned int sidx = s_next;
+        if (sidx >= ns) break;
         if (threadIdx.x < 12) sT[threadIdx.x] = surv[sidx].T[threadIdx.x];
         __syncthreads();
         double T[12];
@@ -446,18 +452,20 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     int stride = (int)(nchunks * 0.618);  // stride coprime with the chunk count (1 when there are < 3 chunks)
     if (stride < 1) stride = 1;
     while (stride > 1 && std::__gcd(stride, nchunks) != 1) stride--;
-    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * (blind ? 1 : 8));
+    static int occ256 = 0;
+    if (!occ256) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ256, k_ransac_validate<256>, 256, 0));
+    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * (blind ? 1 : (occ256 > 0 ? occ256 : 4)));
     const size_t pend_idx = ctx->pending.size();
     {
         KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
         if (blind)
             k_ransac_validate<1024><<<vblocks, 1024, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
                                                                         w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
-                                                                        recs, counters + 1, (unsigned int)cap, stride);
+                                                                        recs, counters + 1, (unsigned int)cap, stride, counters + 2);
         else
             k_ransac_validate<256><<<vblocks, 256, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
                                                                       w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
-                                                                      recs, counters + 1, (unsigned int)cap, stride);
+                                                                      recs, counters + 1, (unsigned int)cap, stride, counters + 2);
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
