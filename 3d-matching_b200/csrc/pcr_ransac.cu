@@ -12,6 +12,7 @@
 //                       1-NN in the target grid, inlier count + fixed-point sum d2 (D5), correspondence
 //                       inlier count; survivors better than the running best are emitted as records.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pcr_common.cuh"
 
@@ -446,26 +447,32 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
                                                                        hyp_begin, count, seed, surv, counters);
         PCR_LAUNCHED();
     }
+    // CTA size: the duration of a wave is bounded below by ONE full evaluation (ceil(ms / threads) sequential rounds of
+    // ~8 us: 290 us for 9k points with 256 threads — measured: the waves ran at 22 % warp occupancy, waiting for such
+    // tails), so larger CTAs shorten every wave; smaller CTAs prune at a finer grain and pack better.
+    static const int vt_env = getenv("PCR_VAL_THREADS") ? atoi(getenv("PCR_VAL_THREADS")) : 0;
     const bool blind = best_cnt <= 0;  // nothing to prune against yet: few survivors, full evaluations
-    const int vthreads = blind ? 1024 : 256;
+    const int vthreads = blind ? 1024 : (vt_env ? vt_env : 512);
     const int nchunks = div_up(ms, vthreads);
     int stride = (int)(nchunks * 0.618);  // stride coprime with the chunk count (1 when there are < 3 chunks)
     if (stride < 1) stride = 1;
     while (stride > 1 && std::__gcd(stride, nchunks) != 1) stride--;
-    static int occ256 = 0;
+    static int occ256 = 0, occ512 = 0;
     if (!occ256) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ256, k_ransac_validate<256>, 256, 0));
-    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * (blind ? 1 : (occ256 > 0 ? occ256 : 4)));
+    if (!occ512) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ512, k_ransac_validate<512>, 512, 0));
+    const int per_sm = vthreads == 1024 ? 1 : (vthreads == 512 ? (occ512 > 0 ? occ512 : 2) : (occ256 > 0 ? occ256 : 4));
+    const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * per_sm);
     const size_t pend_idx = ctx->pending.size();
     {
         KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
-        if (blind)
-            k_ransac_validate<1024><<<vblocks, 1024, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
-                                                                        w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
-                                                                        recs, counters + 1, (unsigned int)cap, stride, counters + 2);
-        else
-            k_ransac_validate<256><<<vblocks, 256, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,
-                                                                      w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq,
-                                                                      recs, counters + 1, (unsigned int)cap, stride, counters + 2);
+#define PCR_VAL_LAUNCH(NT)                                                                                                       \
+        k_ransac_validate<NT><<<vblocks, NT, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist, w.r2, \
+                                                               ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, recs,       \
+                                                               counters + 1, (unsigned int)cap, stride, counters + 2)
+        if (vthreads == 1024) PCR_VAL_LAUNCH(1024);
+        else if (vthreads == 512) PCR_VAL_LAUNCH(512);
+        else PCR_VAL_LAUNCH(256);
+#undef PCR_VAL_LAUNCH
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
@@ -554,7 +561,9 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
     std::vector<pcr_hyp_record> recs;
-    int64_t begin = 0, wave = 2048;  // small blind first wave (no best to prune against yet), then x4 to fill the GPU
+    static const int wave_first = getenv("PCR_WAVE_FIRST") ? atoi(getenv("PCR_WAVE_FIRST")) : 2048;
+    static const int wave_growth = getenv("PCR_WAVE_GROWTH") ? atoi(getenv("PCR_WAVE_GROWTH")) : 8;
+    int64_t begin = 0, wave = wave_first;  // small blind first wave (no best to prune against yet), then growing to fill the GPU
     int64_t survivors = 0;
     while (begin < max_iter && begin < res->est_k) {
         const int64_t end = std::min<int64_t>(max_iter, begin + wave);
@@ -574,7 +583,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
         pcr_ransac_scan(recs.data(), nrec, begin, end, c, ms, confidence, w.k_d, res, &stop);
         begin = end;
         if (stop) break;
-        if (wave < (1 << 20)) wave *= 4;
+        if (wave < (1 << 20)) wave *= wave_growth;
     }
     res->survivors = survivors;
     res->k_d = w.k_d;
