@@ -339,39 +339,138 @@ __global__ void __launch_bounds__(128) k_match_recheck(const float *__restrict__
     }
 }
 
-// exact scan for the rows that failed the certificate (device-side count, no host sync): one CTA per row
-constexpr int FB_THREADS = 256;
-__global__ void __launch_bounds__(FB_THREADS) k_match_fallback(const float *__restrict__ fq, const float *__restrict__ fb, int nb,
+// descriptors [n][33] -> [33][n]: the fallback scan then reads 32 consecutive candidates per load instruction (the
+// row-major layout costs 32 L1 tag look-ups per load and made the scan L1-bound: 142 us for 3.5 % of the rows)
+__global__ void __launch_bounds__(256) k_feat_transpose(const float *__restrict__ f, int n, float *__restrict__ ft) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * 33) return;
+    const int j = (int)(i / 33), k = (int)(i % 33);
+    ft[(size_t)k * n + j] = __ldg(f + i);
+}
+
+// Exact scan for the rows that failed the certificate (device-side count, no host sync).
+// Work item = (row, part): the candidates are cut into FB_PARTS contiguous ranges so that a few hundred rows still fill
+// the machine; the query descriptor is read from shared memory (broadcast) so that the kernel runs at 40 registers.
+//
+// fp32 filter: sum (a_k - b_k)^2 in fp32 has a RELATIVE error below 36 * 2^-24 = 2.2e-6 (no cancellation in this form),
+// so the exact minimiser j* satisfies d32(j*) <= (1 + 7e-6) * d32(j) for every j.  Pass 1 finds the minimum of d32 over
+// the part (coalesced loads from the transposed descriptors, fp32 only); pass 2 re-scores in fp64 (rule D9) only the
+// candidates within 1e-4 of it — a handful — so the fp64 dependency chains, which made the all-fp64 scan latency-bound
+// (142 us for 3.5 % of the rows), all but disappear.  The part minimum is >= the row minimum, so the filter of a part
+// keeps every candidate the row-wide filter would keep; the part that finishes last merges the FB_PARTS exact results
+// with the (distance, index) tie rule.  (A per-thread running minimum does not work: among the 32 lanes of a warp some
+// lane sets a new record in nearly every step, and the warp pays the fp64 path every time.)
+// Pass 1 parks its fp32 distances in shared memory, so pass 2 reads no descriptors at all; the candidates of a row are
+// cut into >= 8 parts so that a few hundred rows give a few thousand work items.
+constexpr int FB_THREADS = 128;
+constexpr int FB_ROWS = 1;  // rows sharing one descriptor sweep (4 was measured slower: too few work items, LDS-heavy)
+constexpr int FB_PER_MAX = 2560;  // candidates per part: FB_ROWS * FB_PER_MAX floats of dynamic shared memory (40 KB)
+struct FbPart {
+    double d;
+    int j;
+    int pad;
+};
+
+__global__ void __launch_bounds__(FB_THREADS) k_match_fallback(const float *__restrict__ fq, const float *__restrict__ fb,
+                                                               const float *__restrict__ fbT, int nb, int nparts, int per,
                                                                const int *__restrict__ rows, const unsigned int *__restrict__ n_rows,
+                                                               FbPart *__restrict__ parts, unsigned int *__restrict__ tickets,
                                                                int *__restrict__ nn) {
+    extern __shared__ float sd32[];  // [FB_ROWS][per]
+    __shared__ float sa[FB_ROWS][33];
     __shared__ double sd[FB_THREADS / 32];
     __shared__ int si[FB_THREADS / 32];
+    __shared__ float sf[FB_ROWS][FB_THREADS / 32];
     const unsigned int n = *n_rows;
+    const unsigned int n_groups = (n + FB_ROWS - 1) / FB_ROWS;
+    const unsigned int n_items = n_groups * (unsigned int)nparts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned int r = blockIdx.x; r < n; r += gridDim.x) {
-        const int q = rows[r];
-        float a[33];
-#pragma unroll
-        for (int k = 0; k < 33; k++) a[k] = __ldg(fq + (size_t)q * 33 + k);
-        double best = INFINITY;
-        int bi = 0x7fffffff;
-        for (int j = threadIdx.x; j < nb; j += FB_THREADS) {
-            const double d = exact_dist(a, fb + (size_t)j * 33);
-            if (d < best) { best = d; bi = j; }  // ascending j per thread: strict < keeps the lowest index
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    for (unsigned int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const unsigned int grp = item / (unsigned int)nparts;
+        const int part = (int)(item % (unsigned int)nparts);
+        const int j0 = part * per, j1 = min(nb, j0 + per);
+        __syncthreads();
+        for (int t = threadIdx.x; t < FB_ROWS * 33; t += FB_THREADS) {
+            const unsigned int r = grp * FB_ROWS + t / 33;
+            sa[t / 33][t % 33] = r < n ? __ldg(fq + (size_t)rows[r] * 33 + t % 33) : 0.0f;
         }
         __syncthreads();
-        if (lane == 0) { sd[warp] = best; si[warp] = bi; }
+        // pass 1: fp32 distances of FB_ROWS rows to every candidate of the part, one descriptor sweep
+        float m32[FB_ROWS];
+#pragma unroll
+        for (int u = 0; u < FB_ROWS; u++) m32[u] = INFINITY;
+        for (int j = j0 + threadIdx.x; j < j1; j += FB_THREADS) {
+            float acc[FB_ROWS];
+#pragma unroll
+            for (int u = 0; u < FB_ROWS; u++) acc[u] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 33; k++) {
+                const float bk = __ldg(fbT + (size_t)k * nb + j);
+#pragma unroll
+                for (int u = 0; u < FB_ROWS; u++) {
+                    const float df = sa[u][k] - bk;
+                    acc[u] = __fmaf_rn(df, df, acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FB_ROWS; u++) {
+                sd32[u * per + (j - j0)] = acc[u];
+                m32[u] = fminf(m32[u], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FB_ROWS; u++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m32[u] = fminf(m32[u], __shfl_xor_sync(0xffffffffu, m32[u], o));
+            if (lane == 0) sf[u][warp] = m32[u];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < FB_THREADS / 32; w++)
-                if (sd[w] < best || (sd[w] == best && si[w] < bi)) { best = sd[w]; bi = si[w]; }
-            nn[q] = bi;
+        // pass 2, row by row: exact fp64 re-score of the candidates within 1e-4 of the part minimum
+        for (int u = 0; u < FB_ROWS; u++) {
+            const unsigned int r = grp * FB_ROWS + u;
+            if (r >= n) break;  // block-uniform
+            float m = sf[u][0];
+#pragma unroll
+            for (int w = 1; w < FB_THREADS / 32; w++) m = fminf(m, sf[u][w]);
+            const float lim = m * 1.0001f;
+            double best = INFINITY;
+            int bi = 0x7fffffff;
+            for (int j = j0 + threadIdx.x; j < j1; j += FB_THREADS) {
+                if (sd32[u * per + (j - j0)] <= lim) {
+                    const double d = exact_dist(sa[u], fb + (size_t)j * 33);
+                    if (d < best) { best = d; bi = j; }  // ascending j per thread: strict < keeps the lowest index
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+            }
+            __syncthreads();
+            if (lane == 0) { sd[warp] = best; si[warp] = bi; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < FB_THREADS / 32; w++)
+                    if (sd[w] < best || (sd[w] == best && si[w] < bi)) { best = sd[w]; bi = si[w]; }
+                FbPart *o = parts + (size_t)r * nparts + part;
+                o->d = best;
+                o->j = bi;
+                __threadfence();
+                const unsigned int t = atomicAdd(tickets + r, 1u);
+                if (t == (unsigned int)nparts - 1u) {  // last part of this row: merge with the (distance, index) rule
+                    __threadfence();
+                    const volatile FbPart *v = parts + (size_t)r * nparts;
+                    double bd = v[0].d;
+                    int bj = v[0].j;
+                    for (int p2 = 1; p2 < nparts; p2++) {
+                        const double d2 = v[p2].d;
+                        const int jj = v[p2].j;
+                        if (d2 < bd || (d2 == bd && jj < bj)) { bd = d2; bj = jj; }
+                    }
+                    nn[rows[r]] = bj;
+                }
+            }
         }
     }
 }
@@ -412,6 +511,18 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
         PCR_TRY(tc_prep(ctx, fq, nq, 0, &A));
         PCR_TRY(tc_prep(ctx, fb, nb, 1, &B));
     }
+    PCR_ALLOC(fbT, float, (size_t)nb * 33);
+    int fb_nparts = div_up(nb, FB_PER_MAX);
+    if (fb_nparts < 8) fb_nparts = 8;
+    const int fb_per = div_up(nb, fb_nparts);
+    PCR_ALLOC(fb_parts, FbPart, (size_t)nq * fb_nparts);
+    PCR_ALLOC(fb_tickets, unsigned int, (size_t)nq);
+    PCR_CUDA(cudaMemsetAsync(fb_tickets, 0, sizeof(unsigned int) * (size_t)nq, ctx->stream));
+    {
+        KScope ks(ctx, KC_MATCH_MISC, 264.0 * nb);
+        k_feat_transpose<<<div_up((long long)nb * 33, 256), 256, 0, ctx->stream>>>(fb, nb, fbT);
+        PCR_LAUNCHED();
+    }
     // slices of the base rows so that the grid covers the machine
     // long column streams keep the top-4 insertions rare: only as many slices as needed to occupy the SMs
     int n_split = 1;
@@ -441,7 +552,8 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
         k_match_recheck<<<div_up((long long)nq * 32, 128), 128, 0, ctx->stream>>>(fq, nq, fb, nb, cand_idx, cand_kth, n_lists, B.max_bits, nn, fb_rows,
                                                                   n_fb);
         PCR_LAUNCHED();
-        k_match_fallback<<<ctx->sm_count * 4, FB_THREADS, 0, ctx->stream>>>(fq, fb, nb, fb_rows, n_fb, nn);
+        k_match_fallback<<<ctx->sm_count * 12, FB_THREADS, sizeof(float) * FB_ROWS * (size_t)fb_per, ctx->stream>>>(
+            fq, fb, fbT, nb, fb_nparts, fb_per, fb_rows, n_fb, fb_parts, fb_tickets, nn);
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
