@@ -234,9 +234,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_list(const float4 *__res
 
 // ---- MODE_NORMAL: covariance of the neighbourhood (A.2 cumulants, sequential in neighbour order) -----------------
 // cov_out: 6 doubles per query (c00 c01 c02 c11 c12 c22); the eigen-solve runs one query per thread afterwards.
-__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__restrict__ pts, int n, Grid g, float r2,
-                                                            int max_nn, double *__restrict__ cov_out) {
-    __shared__ u64 sbuf[KNN_WARPS][KNN_CAP];
+// TOP32 = true: max_nn <= 32, register-resident list; shared memory only stages the 32 x 9 products of a warp (2.3 KB),
+// so the kernel is limited by its 61 registers (8 CTAs / SM) instead of by the 8 KB-per-warp list buffer (6 CTAs / SM).
+template <bool TOP32>
+__global__ void __launch_bounds__(KNN_WARPS * 32, TOP32 ? 8 : 4) k_knn_cov(const float4 *__restrict__ pts, int n, Grid g, float r2,
+                                                                            int max_nn, double *__restrict__ cov_out) {
+    __shared__ u64 sbuf[KNN_WARPS][TOP32 ? 288 : KNN_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *buf = sbuf[warp];
     for (int q = blockIdx.x * KNN_WARPS + warp; q < n; q += gridDim.x * KNN_WARPS) {
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_cov(const float4 *__rest
         const int ib = lane < 3 ? 0 : (lane < 6 ? lane - 2 : (lane < 8 ? lane - 4 : 3));
         int c;
         double cu = 0.0;
-        if (max_nn <= 32) {  // warp-uniform
+        if (TOP32) {
             u64 mine;
             c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
             // lane k fetches neighbour k (all gathers in flight together) and writes its nine products to shared
@@ -581,7 +584,10 @@ int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int 
     PCR_ALLOC(cov, double, (size_t)n * 6);
     {
         KScope ks(ctx, KC_KNN_COV, 32.0 * n + 48.0 * n);
-        k_knn_cov<<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+        if (max_nn <= 32)
+            k_knn_cov<true><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+        else
+            k_knn_cov<false><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
         PCR_LAUNCHED();
     }
     {
