@@ -31,8 +31,15 @@ for p in (ROOT, os.path.join(ROOT, "3d-matching_b200")):
 
 import numpy as np  # noqa: E402
 
-# keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-os.environ["NCCL_DEBUG"] = "WARN"
+# Keep stdout to the single JSON line: libraries (NCCL's version banner, for one) write to file descriptor 1 directly.
+# Everything this process prints goes to stderr; the JSON line is written to the saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def host_threads():
@@ -155,7 +162,7 @@ def run_reference(args):
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "result": {"fitness": i.fitness, "inlier_rmse": i.inlier_rmse, "ransac_best_hyp": r.best_hyp},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -322,7 +329,7 @@ def run_engine(args):
                        "max_abs_T_err_vs_truth": float(np.abs(np.array(icp_r.transformation).reshape(4, 4) - T_true).max())},
             "aux": aux,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -230,6 +230,24 @@ def test_icp(orc, eng, pair, iters, rf, rr):
     assert g.fitness == o.fitness and g.inlier_rmse == o.inlier_rmse
 
 
+def test_icp_certified_passes_ties_and_drift(orc, eng, pair):
+    """Many passes (the certified streaming path runs from pass 3 on), a start far enough that correspondences appear,
+    change and drop out while the cloud moves, and a target with exact duplicates (ties decided by the lowest index):
+    correspondences, sums and the transform must still equal a search in every pass (the oracle) bit for bit."""
+    v = pair["v"]
+    tgt = np.concatenate([pair["tgt"], pair["tgt"][:700], pair["tgt"][100:300]])
+    otn = orc.estimate_normals(tgt, 2 * v, 30)
+    pert = np.eye(4); pert[:3, :3] = synth.euler_zyx(0.012, -0.009, 0.007); pert[:3, 3] = [1.5e-3, -1.1e-3, 0.9e-3]
+    init = pert @ pair["T"]
+    for iters in (3, 41):
+        g, corr = eng.icp_point_to_plane(pair["ds"], eng.pack(tgt), eng.pack(otn), 0.4 * v, init, iters, 0.0, 0.0)
+        o = orc.icp_point_to_plane(pair["src"], tgt, otn, 0.4 * v, init, iters, 0.0, 0.0)
+        assert np.array_equal(corr.cpu().numpy(), o.correspondence)
+        assert (g.inlier_count, g.sum_d2_fixed, g.iterations) == (o.inlier_count, o.sum_d2_fixed, o.iterations)
+        assert np.array_equal(g.transformation, o.transformation)
+    assert 0.2 < g.fitness < 1.0
+
+
 def test_icp_edge_cases(eng, pair):
     v = pair["v"]
     n = eng.pack(np.tile([[0, 0, 1.0]], (pair["dt"].shape[0], 1)))
