@@ -19,14 +19,10 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
 int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, const int *corr, int c,
                     double max_dist, double edge_sim, int64_t max_iter, double confidence, u64 seed,
                     pcr_reg_result *res);
-struct RansacWork {
-    Grid g;
-    const float4 *src_sorted;
-    float r2;
-    int k_d;
-};
 int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist,
                        RansacWork *w);
+int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist);
+int pcr_ransac_session_end_impl(pcr_ctx *ctx);
 int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt,
                          const int *corr, int c, double max_dist, double edge_sim, long long hyp_begin,
                          long long hyp_end, u64 seed, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
@@ -122,12 +118,27 @@ int pcr_ransac_wave(pcr_ctx *ctx, const float *src, int ms, const float *tgt, in
     PCR_ENTER();
     PCR_ARG(ms > 0 && mt > 0 && c >= 3 && max_dist > 0.0 && records && cap > 0 && n_records && n_survivors);
     RansacWork w;
-    PCR_TRY(pcr_ransac_prepare(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, max_dist, &w));
+    const auto &rs = ctx->rsess;
+    if (rs.active && rs.src == (const void *)src && rs.tgt == (const void *)tgt && rs.ms == ms && rs.mt == mt && rs.max_dist == max_dist)
+        w = rs.w;  // inside a session on these clouds: the grid and the sorted source are already there
+    else
+        PCR_TRY(pcr_ransac_prepare(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, max_dist, &w));
     long long ns = 0;
     const int rc = pcr_ransac_wave_impl(ctx, w, (const float4 *)src, ms, (const float4 *)tgt, corr, c, max_dist, edge_sim,
                                         hyp_begin, hyp_end, seed, best_count, best_sum, records, cap, n_records, &ns);
     *n_survivors = ns;
     return rc;
+}
+
+int pcr_ransac_session_begin(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt, double max_dist) {
+    PCR_ENTER();
+    PCR_ARG(ms > 0 && mt > 0 && max_dist > 0.0);
+    return pcr_ransac_session_begin_impl(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, max_dist);
+}
+
+int pcr_ransac_session_end(pcr_ctx *ctx) {
+    PCR_ENTER();
+    return pcr_ransac_session_end_impl(ctx);
 }
 
 int pcr_ransac_step(pcr_ctx *ctx, const float *src, const float *tgt, const int *corr, int c, uint64_t seed,

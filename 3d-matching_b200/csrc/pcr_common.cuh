@@ -30,6 +30,29 @@ struct KPending {
     long long launches;
 };
 
+// ---- uniform grid -----------------------------------------------------------------------------------
+// Dense grid over the bounding box of the indexed cloud; cells ordered x-fastest so that the three
+// x-neighbours of a cell are one contiguous range of the sorted point array.
+struct Grid {
+    const float4 *sorted;   // points sorted by cell; .w = original index (int bits)
+    const uint32_t *start;  // ncells+1 exclusive prefix
+    double ox, oy, oz;      // origin (min bound)
+    double inv_h;           // 1 / cell size
+    double h;
+    int nx, ny, nz;
+    int n;
+    int R;                  // rings of cells that cover the search radius (1 unless built by pcr_grid_build_rings)
+};
+
+
+// prepared RANSAC work (target grid + spatially sorted source), see pcr_ransac.cu
+struct RansacWork {
+    Grid g;
+    const float4 *src_sorted;
+    float r2;
+    int k_d;
+};
+
 struct pcr_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -53,6 +76,16 @@ struct pcr_ctx {
     // bounding boxes already reduced during the current exported call, keyed by (pointer, n); cleared on entry
     struct BoundsEntry { const void *ptr; int n; float lo[3], hi[3]; };
     std::vector<BoundsEntry> bounds_cache;
+    // RANSAC session (pcr_ransac_session_begin/end): prepared work in buffers that outlive the per-call arena
+    struct RansacSession {
+        bool active = false;
+        const void *src = nullptr, *tgt = nullptr;
+        int ms = 0, mt = 0;
+        double max_dist = 0.0;
+        RansacWork w;
+        void *bufs[3] = {nullptr, nullptr, nullptr};  // grid.sorted, grid.start, src_sorted (grow-only, freed at destroy)
+        size_t cap[3] = {0, 0, 0};
+    } rsess;
 };
 
 extern std::atomic<long long> g_pcr_launches;
@@ -103,20 +136,6 @@ static inline int pcr_ilog2ceil(long long n) {
     return e;
 }
 int pcr_pow2ceil_exp(double x);  // smallest e with 2^e >= x
-
-// ---- uniform grid -----------------------------------------------------------------------------------
-// Dense grid over the bounding box of the indexed cloud; cells ordered x-fastest so that the three
-// x-neighbours of a cell are one contiguous range of the sorted point array.
-struct Grid {
-    const float4 *sorted;   // points sorted by cell; .w = original index (int bits)
-    const uint32_t *start;  // ncells+1 exclusive prefix
-    double ox, oy, oz;      // origin (min bound)
-    double inv_h;           // 1 / cell size
-    double h;
-    int nx, ny, nz;
-    int n;
-    int R;                  // rings of cells that cover the search radius (1 unless built by pcr_grid_build_rings)
-};
 
 // bounds: lo/hi (host) of a float4 cloud; one device reduction + one D2H sync
 int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]);

@@ -138,6 +138,8 @@ int pcr_destroy(pcr_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (void *b : ctx->blocks) cudaFree(b);
+    for (void *b : ctx->rsess.bufs)
+        if (b) cudaFree(b);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -12,6 +12,7 @@
 //                       1-NN in the target grid, inlier count + fixed-point sum d2 (D5), correspondence
 //                       inlier count; survivors better than the running best are emitted as records.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "pcr_common.cuh"
@@ -167,7 +168,10 @@ __device__ void rigid3(const double s[3][3], const double t[3][3], double *T) {
 struct Survivor {
     long long hyp;
     double T[12];
+    long long f_cnt, f_sumq;  // totals of a completed evaluation (valid once published through bucket_best)
 };
+
+constexpr int VAL_BUCKETS = 64;  // hypothesis-index buckets of a wave for the in-wave sharing of bests
 
 __device__ __forceinline__ void gather3(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
                                         const int2 *__restrict__ corr, const int id[3], double s[3][3], double t[3][3]) {
@@ -226,16 +230,50 @@ __global__ void __launch_bounds__(128) k_ransac_generate(const float4 *__restric
 // of chunks), so that the first few chunks already sample the whole cloud: the misses of a slightly-off hypothesis,
 // which cluster at the far ends of the object, are seen early and the exact pruning rule fires after a few chunks
 // instead of most of them.  The pruning rule itself does not depend on the order.
+// IsBetterRANSACThan: (c1, s1) strictly better than (c0, s0)
+__device__ __forceinline__ bool ransac_better(long long c1, long long s1, long long c0, long long s0) {
+    return c1 > c0 || (c1 == c0 && c0 > 0 && s1 < s0);
+}
+
+// Best score among (a) the running best at wave start and (b) the completed survivors of EARLIER hypothesis buckets of
+// this wave (warp-cooperative; every lane returns the result).  A hypothesis h may be pruned against any hypothesis
+// g < h: when the sequential loop reaches h it holds a best at least as good as g's, so h is a prefix maximum only if it
+// beats g.  bucket_best[b] is the index of the best completed survivor of bucket b (-1: none yet); a survivor is
+// published (totals, fence, compare-and-swap of the index) only after its full evaluation, so a reader always sees
+// consistent totals.
+__device__ __forceinline__ void ransac_effective_best(const Survivor *surv, const int *bucket_best, int my_bucket, int lane,
+                                                      long long best_cnt, long long best_sumq, long long *oc, long long *os) {
+    long long c = best_cnt, q = best_sumq;
+    for (int b = lane; b < my_bucket; b += 32) {
+        const int idx = *(volatile const int *)(bucket_best + b);
+        if (idx >= 0) {
+            const long long c1 = *(volatile const long long *)&surv[idx].f_cnt;
+            const long long q1 = *(volatile const long long *)&surv[idx].f_sumq;
+            if (ransac_better(c1, q1, c, q)) { c = c1; q = q1; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long c1 = __shfl_xor_sync(0xffffffffu, c, o), q1 = __shfl_xor_sync(0xffffffffu, q, o);
+        if (ransac_better(c1, q1, c, q)) { c = c1; q = q1; }
+    }
+    *oc = c;
+    *os = q;
+}
+
 template <int VAL_THREADS>
 __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g, const int2 *__restrict__ corr, int c,
-    double max_dist, float r2, double sc_d, const Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
+    double max_dist, float r2, double sc_d, Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
     long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs, unsigned int *__restrict__ n_recs,
-    unsigned int rec_cap, int chunk_stride, unsigned int *__restrict__ next_surv) {
+    unsigned int rec_cap, int chunk_stride, unsigned int *__restrict__ next_surv, int *__restrict__ bucket_best,
+    long long hyp_begin, long long hyp_count) {
     __shared__ double sT[12];
     __shared__ long long red[VAL_THREADS / 32][3];
+    __shared__ long long s_best[2];
     __shared__ unsigned int s_next;
     const unsigned int ns = *n_surv;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // survivors are handed out dynamically: evaluations range from one chunk (pruned) to the whole cloud
     for (;;) {
         __syncthreads();
@@ -244,21 +282,24 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
         const unsigned int sidx = s_next;
         if (sidx >= ns) break;
         if (threadIdx.x < 12) sT[threadIdx.x] = surv[sidx].T[threadIdx.x];
+        const int my_bucket = (int)(((surv[sidx].hyp - hyp_begin) * VAL_BUCKETS) / hyp_count);
         __syncthreads();
-        double T[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++) T[i] = sT[i];
+        const double *T = sT;  // broadcast shared-memory reads
         long long cnt = 0, sumq = 0, cin = 0;
-        // Exact pruning against the running best at wave start (a lower bound of the best the sequential loop
-        // holds when it reaches this hypothesis): stop as soon as the survivor can no longer be an improvement —
-        // its count cannot reach the best count, or it can at most tie the count while its sum of squared
-        // distances (which only grows) already reaches the best sum.  found/partial sums are block-uniform.
+        // Exact pruning against the effective best (above): stop as soon as the survivor can no longer be an
+        // improvement — its count cannot reach the best count, or it can at most tie the count while its sum of
+        // squared distances (which only grows) already reaches the best sum.  All quantities are block-uniform.
         int found = 0;
         long long partial = 0;
         bool pruned = false;
         const int nchunks = (ms + VAL_THREADS - 1) / VAL_THREADS;
         int done_pts = 0, chunk = 0;
         for (int kc = 0; kc < nchunks; kc++) {
+            if ((kc & 3) == 0 && warp == 0) {  // refresh the effective best every 4 chunks (visible after the barriers below)
+                long long ec, es;
+                ransac_effective_best(surv, bucket_best, my_bucket, lane, best_cnt, best_sumq, &ec, &es);
+                if (lane == 0) { s_best[0] = ec; s_best[1] = es; }
+            }
             const int base = chunk * VAL_THREADS;
             chunk += chunk_stride;
             if (chunk >= nchunks) chunk -= nchunks;
@@ -266,43 +307,65 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
             const int i = base + threadIdx.x;
             bool hit = false;
             long long q_add = 0;
-            {
-                const bool valid = i < ms;
-                const float4 p = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < ms) {
+                const float4 p = __ldg(src + i);
                 const float3 q = xform_pt(T, p.x, p.y, p.z);
                 float d2;
-                const int j = valid ? grid_nn1(g, q.x, q.y, q.z, r2, &d2) : -1;
-                if (j >= 0) {
+                if (grid_nn1(g, q.x, q.y, q.z, r2, &d2) >= 0) {
                     hit = true;
                     cnt++;
                     q_add = fixed_ll((double)d2, sc_d);
                     sumq += q_add;
                 }
             }
+            const long long w = warp_sum_ll(q_add);
+            if (lane == 0) red[warp][0] = w;
             found += __syncthreads_count(hit);
-            const int remaining = ms - done_pts;
-            if ((long long)found + remaining < best_cnt) {
+            long long tot = 0;
+#pragma unroll
+            for (int k = 0; k < VAL_THREADS / 32; k++) tot += red[k][0];
+            partial += tot;
+            const long long e_cnt = s_best[0], e_sumq = s_best[1];
+            __syncthreads();  // red / s_best are rewritten in the next round
+            const long long reachable = (long long)found + (ms - done_pts);
+            if (reachable < e_cnt || (e_cnt > 0 && reachable == e_cnt && partial >= e_sumq)) {
                 pruned = true;
                 break;
             }
-            if (best_cnt > 0 && (long long)found + remaining == best_cnt) {
-                // only a tie on count is still possible: compare the partial sum (block-wide) with the best sum
-                const long long w = warp_sum_ll(q_add);
-                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][0] = w;
-                __syncthreads();
-                long long tot = 0;
-#pragma unroll
-                for (int k = 0; k < VAL_THREADS / 32; k++) tot += red[k][0];
-                partial += tot;
-                __syncthreads();
-                if (partial >= best_sumq) {
-                    pruned = true;
-                    break;
-                }
-            }  // chunks scored before the tie regime began are not in `partial`: it is a lower bound, which keeps
-               // the test conservative
         }
         if (pruned) continue;  // block-uniform
+        cnt = warp_sum_ll(cnt);
+        sumq = warp_sum_ll(sumq);
+        if (lane == 0) {
+            red[warp][0] = cnt;
+            red[warp][1] = sumq;
+        }
+        if (warp == 0) {
+            long long ec, es;
+            ransac_effective_best(surv, bucket_best, my_bucket, lane, best_cnt, best_sumq, &ec, &es);
+            if (lane == 0) { s_best[0] = ec; s_best[1] = es; }
+        }
+        __syncthreads();
+        long long a = 0, b = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < VAL_THREADS / 32; w2++) { a += red[w2][0]; b += red[w2][1]; }
+        // a necessary condition for being a prefix maximum of the sequential loop (block-uniform)
+        const bool better = ransac_better(a, b, s_best[0], s_best[1]);
+        if (threadIdx.x == 0) {
+            // publish the completed evaluation to this wave's later buckets
+            surv[sidx].f_cnt = a;
+            surv[sidx].f_sumq = b;
+            __threadfence();
+            int cur = *(volatile int *)(bucket_best + my_bucket);
+            for (;;) {
+                if (cur >= 0 && !ransac_better(a, b, *(volatile long long *)&surv[cur].f_cnt, *(volatile long long *)&surv[cur].f_sumq)) break;
+                const int old = atomicCAS(bucket_best + my_bucket, cur, (int)sidx);
+                if (old == cur) break;
+                cur = old;
+            }
+        }
+        if (!better) continue;
+        // correspondence-set inliers (only records need them: the early-exit estimate of the host replay)
         for (int i = threadIdx.x; i < c; i += VAL_THREADS) {
             const int2 cc = __ldg(corr + i);
             const float4 p = __ldg(src_orig + cc.x), q = __ldg(tgt + cc.y);
@@ -312,34 +375,24 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
             const double dz = (((T[8] * x + T[9] * y) + T[10] * z) + T[11]) - (double)q.z;
             if (sqrt((dx * dx + dy * dy) + dz * dz) < max_dist) cin++;
         }
-        cnt = warp_sum_ll(cnt);
-        sumq = warp_sum_ll(sumq);
         cin = warp_sum_ll(cin);
-        if ((threadIdx.x & 31) == 0) {
-            red[threadIdx.x >> 5][0] = cnt;
-            red[threadIdx.x >> 5][1] = sumq;
-            red[threadIdx.x >> 5][2] = cin;
-        }
+        __syncthreads();
+        if (lane == 0) red[warp][2] = cin;
         __syncthreads();
         if (threadIdx.x == 0) {
-            long long a = 0, b = 0, d = 0;
+            long long d = 0;
 #pragma unroll
-            for (int w = 0; w < VAL_THREADS / 32; w++) { a += red[w][0]; b += red[w][1]; d += red[w][2]; }
-            // IsBetterRANSACThan against the running best at wave start (a necessary condition for being a
-            // prefix maximum of the sequential loop)
-            const bool better = a > best_cnt || (a == best_cnt && best_cnt > 0 && b < best_sumq);
-            if (better) {
-                const unsigned int slot = atomicAdd(n_recs, 1u);
-                if (slot < rec_cap) {
-                    pcr_hyp_record *o = recs + slot;
-                    o->hyp = surv[sidx].hyp;
-                    o->inlier_count = a;
-                    o->sum_d2_fixed = b;
-                    o->corr_inliers = (int)d;
-                    o->reserved = 0;
+            for (int w2 = 0; w2 < VAL_THREADS / 32; w2++) d += red[w2][2];
+            const unsigned int slot = atomicAdd(n_recs, 1u);
+            if (slot < rec_cap) {
+                pcr_hyp_record *o = recs + slot;
+                o->hyp = surv[sidx].hyp;
+                o->inlier_count = a;
+                o->sum_d2_fixed = b;
+                o->corr_inliers = (int)d;
+                o->reserved = 0;
 #pragma unroll
-                    for (int i = 0; i < 12; i++) o->transformation[i] = sT[i];
-                }
+                for (int i = 0; i < 12; i++) o->transformation[i] = sT[i];
             }
         }
     }
@@ -405,13 +458,6 @@ extern "C" int pcr_ransac_k_d(double max_dist, int ms) {
     return 62 - 2 * pcr_pow2ceil_exp(max_dist) - pcr_ilog2ceil(ms > 1 ? ms : 1);
 }
 
-struct RansacWork {
-    Grid g;
-    const float4 *src_sorted;
-    float r2;
-    int k_d;
-};
-
 int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist,
                        RansacWork *w) {
     PCR_TRY(pcr_grid_build(ctx, tgt, mt, max_dist, nullptr, nullptr, &w->g));
@@ -419,6 +465,39 @@ int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tg
     PCR_TRY(pcr_morton_sort(ctx, src, ms, &w->src_sorted));
     w->r2 = (float)(max_dist * max_dist);
     w->k_d = pcr_ransac_k_d(max_dist, ms);
+    return PCR_OK;
+}
+
+// ---- session: prepared work copied out of the per-call arena ------------------------------------------------------
+int pcr_ransac_session_end_impl(pcr_ctx *ctx) {
+    ctx->rsess.active = false;  // the buffers are kept for the next session (cudaFree would synchronise the device)
+    return PCR_OK;
+}
+
+int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist) {
+    pcr_ransac_session_end_impl(ctx);
+    RansacWork w;
+    PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
+    const size_t ncells = (size_t)w.g.nx * w.g.ny * w.g.nz;
+    const size_t bytes[3] = {sizeof(float4) * (size_t)mt, sizeof(uint32_t) * (ncells + 1), sizeof(float4) * (size_t)ms};
+    const void *from[3] = {w.g.sorted, w.g.start, w.src_sorted};
+    for (int i = 0; i < 3; i++) {
+        if (ctx->rsess.cap[i] < bytes[i]) {
+            if (ctx->rsess.bufs[i]) PCR_CUDA(cudaFree(ctx->rsess.bufs[i]));
+            ctx->rsess.bufs[i] = nullptr;
+            ctx->rsess.cap[i] = 0;
+            PCR_CUDA(cudaMalloc(&ctx->rsess.bufs[i], bytes[i] + bytes[i] / 4));
+            ctx->rsess.cap[i] = bytes[i] + bytes[i] / 4;
+        }
+        PCR_CUDA(cudaMemcpyAsync(ctx->rsess.bufs[i], from[i], bytes[i], cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));  // the arena copies may be recycled by the next call
+    w.g.sorted = (const float4 *)ctx->rsess.bufs[0];
+    w.g.start = (const uint32_t *)ctx->rsess.bufs[1];
+    w.src_sorted = (const float4 *)ctx->rsess.bufs[2];
+    ctx->rsess.w = w;
+    ctx->rsess.src = src; ctx->rsess.tgt = tgt; ctx->rsess.ms = ms; ctx->rsess.mt = mt; ctx->rsess.max_dist = max_dist;
+    ctx->rsess.active = true;
     return PCR_OK;
 }
 
@@ -441,6 +520,8 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     unsigned int *counters = (unsigned int *)hdr;
     pcr_hyp_record *recs = (pcr_hyp_record *)(hdr + 16);
     PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
+    PCR_ALLOC(bucket_best, int, VAL_BUCKETS);
+    PCR_CUDA(cudaMemsetAsync(bucket_best, 0xff, VAL_BUCKETS * sizeof(int), ctx->stream));
     {
         KScope ks(ctx, KC_RANSAC_GENERATE, 120.0 * (double)count);
         k_ransac_generate<<<div_up(count, 128), 128, 0, ctx->stream>>>(src, tgt, (const int2 *)corr, c, max_dist, edge_sim,
@@ -452,7 +533,9 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     // tails), so larger CTAs shorten every wave; smaller CTAs prune at a finer grain and pack better.
     static const int vt_env = getenv("PCR_VAL_THREADS") ? atoi(getenv("PCR_VAL_THREADS")) : 0;
     const bool blind = best_cnt <= 0;  // nothing to prune against yet: few survivors, full evaluations
-    const int vthreads = blind ? 1024 : (vt_env ? vt_env : 512);
+    // measured: 512 threads win on small waves (latency of the few full evaluations), 256 on large, throughput-bound
+    // waves (finer pruning granularity, better packing)
+    const int vthreads = blind ? 1024 : (vt_env ? vt_env : (count >= 65536 ? 256 : 512));
     const int nchunks = div_up(ms, vthreads);
     int stride = (int)(nchunks * 0.618);  // stride coprime with the chunk count (1 when there are < 3 chunks)
     if (stride < 1) stride = 1;
@@ -463,12 +546,20 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     const int per_sm = vthreads == 1024 ? 1 : (vthreads == 512 ? (occ512 > 0 ? occ512 : 2) : (occ256 > 0 ? occ256 : 4));
     const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * per_sm);
     const size_t pend_idx = ctx->pending.size();
+    static const bool dbg = getenv("PCR_DEBUG") != nullptr;
+    cudaEvent_t dbg_a = nullptr, dbg_b = nullptr;
+    if (dbg) {
+        cudaEventCreate(&dbg_a);
+        cudaEventCreate(&dbg_b);
+        cudaEventRecord(dbg_a, ctx->stream);
+    }
     {
         KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
 #define PCR_VAL_LAUNCH(NT)                                                                                                       \
         k_ransac_validate<NT><<<vblocks, NT, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist, w.r2, \
                                                                ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, recs,       \
-                                                               counters + 1, (unsigned int)cap, stride, counters + 2)
+                                                               counters + 1, (unsigned int)cap, stride, counters + 2, bucket_best,    \
+                                                               hyp_begin, count)
         if (vthreads == 1024) PCR_VAL_LAUNCH(1024);
         else if (vthreads == 512) PCR_VAL_LAUNCH(512);
         else PCR_VAL_LAUNCH(256);
@@ -476,12 +567,21 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
+    if (dbg) cudaEventRecord(dbg_b, ctx->stream);
     unsigned char *hp = (unsigned char *)ctx->pinned;
     const int first = cap < FIRST ? cap : FIRST;
     PCR_CUDA(cudaMemcpyAsync(hp, hdr, 16 + sizeof(pcr_hyp_record) * (size_t)first, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned int *hc = (const unsigned int *)hp;
     *n_surv_host = hc[0];
+    if (dbg) {
+        float ms_v = 0.0f;
+        cudaEventElapsedTime(&ms_v, dbg_a, dbg_b);
+        fprintf(stderr, "[pcr ransac] wave [%lld, %lld): %u survivors, %u records, validate %.1f us (%d threads, %d CTAs, best_cnt %lld)\n",
+                hyp_begin, hyp_end, hc[0], hc[1], ms_v * 1e3, vthreads, vblocks, best_cnt);
+        cudaEventDestroy(dbg_a);
+        cudaEventDestroy(dbg_b);
+    }
     // algorithmic bytes of the validation launch: per survivor 16 M_s (source) + 16 M_t (target) + 8 C (pairs)
     if (ctx->profiling && pend_idx < ctx->pending.size())
         ctx->pending[pend_idx].bytes = (double)hc[0] * (16.0 * ms + 16.0 * w.g.n + 8.0 * c);

@@ -90,7 +90,7 @@ EXPORTS = [
     "pcr_pack_xyz_f32", "pcr_pack_xyz_f64", "pcr_unpack_xyz_f32", "pcr_transform_points",
     "pcr_voxel_downsample", "pcr_estimate_normals", "pcr_compute_fpfh", "pcr_knn_hybrid", "pcr_nn1",
     "pcr_match_features", "pcr_nn_features",
-    "pcr_ransac", "pcr_ransac_wave", "pcr_ransac_scan", "pcr_ransac_k_d",
+    "pcr_ransac", "pcr_ransac_wave", "pcr_ransac_session_begin", "pcr_ransac_session_end", "pcr_ransac_scan", "pcr_ransac_k_d",
     "pcr_ransac_step", "pcr_inlier_count",
     "pcr_icp_point_to_plane",
     "pcr_align_default_params", "pcr_align", "pcr_align_host",

@@ -12,6 +12,9 @@ Single-pair ICP stays on one GPU ("replicas only").
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
+import time
 
 import numpy as np
 import torch
@@ -56,6 +59,10 @@ def slice_bounds(begin: int, end: int, rank: int, world: int):
     return begin + n * rank // world, begin + n * (rank + 1) // world
 
 
+FIXED_CAP = 24    # records per rank carried by the per-wave all-gather
+WAVE_GROWTH = 2   # measured: x8 (fewer, larger waves) is slower at 2M hypotheses - the pruning bound of a wave is the best of the earlier waves
+
+
 def ransac_distributed(wave_fn, n_corr: int, n_src: int, k_d: int, max_iter: int, confidence: float, *,
                        group=None, device=None, first_wave: int = 4096, max_wave: int = 1 << 22, lib=None):
     """Generic driver.  wave_fn(lo, hi, best_count, best_sum) -> (n,16) int64 records sorted by hypothesis index
@@ -72,31 +79,45 @@ def ransac_distributed(wave_fn, n_corr: int, n_src: int, k_d: int, max_iter: int
     wave = first_wave * world
     survivors = 0
     waves = 0
+    trace = os.environ.get("PCR_DIST_TRACE") and rank == 0
     while begin < max_iter and begin < state.est_k:
         end = min(max_iter, begin + wave)
         lo, hi = slice_bounds(begin, end, rank, world)
+        t0 = time.perf_counter()
         arr, nsurv = wave_fn(lo, hi, int(state.inlier_count), int(state.sum_d2_fixed))
+        t1 = time.perf_counter()
         chain = prefix_maxima(arr, int(state.inlier_count), int(state.sum_d2_fixed))
         if world > 1:
-            meta = torch.tensor([chain.shape[0], nsurv], dtype=torch.int64, device=device)
-            metas = torch.empty((world * 2,), dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(metas, meta, group=group)
-            metas_h = metas.cpu().numpy().reshape(world, 2)
-            cap = int(metas_h[:, 0].max())
-            survivors += int(metas_h[:, 1].sum())
-            if cap > 0:
+            # ONE all-gather per wave in the common case: [count, survivors, FIXED_CAP records] per rank (a chain of
+            # prefix maxima is ~ln(n) long); a second one only if some rank's chain does not fit
+            buf = np.zeros((2 + FIXED_CAP * REC_WORDS,), np.int64)
+            buf[0], buf[1] = chain.shape[0], nsurv
+            k = min(chain.shape[0], FIXED_CAP)
+            buf[2:2 + k * REC_WORDS] = chain[:k].reshape(-1)
+            mine = torch.from_numpy(buf).to(device)
+            allb = torch.empty((world * buf.shape[0],), dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(allb, mine, group=group)
+            allb_h = allb.cpu().numpy().reshape(world, buf.shape[0])
+            counts = allb_h[:, 0].astype(np.int64)
+            survivors += int(allb_h[:, 1].sum())
+            cap = int(counts.max())
+            if cap <= FIXED_CAP:
+                merged = np.concatenate([allb_h[r, 2:2 + int(counts[r]) * REC_WORDS].reshape(-1, REC_WORDS)
+                                         for r in range(world)], axis=0)
+            else:
                 pad = np.zeros((cap, REC_WORDS), np.int64)
                 pad[: chain.shape[0]] = chain
                 mine = torch.from_numpy(pad.reshape(-1)).to(device)
                 allr = torch.empty((world * cap * REC_WORDS,), dtype=torch.int64, device=device)
                 dist.all_gather_into_tensor(allr, mine, group=group)
                 allr_h = allr.cpu().numpy().reshape(world, cap, REC_WORDS)
-                merged = np.concatenate([allr_h[r, : int(metas_h[r, 0])] for r in range(world)], axis=0)
-            else:
-                merged = np.zeros((0, REC_WORDS), np.int64)
+                merged = np.concatenate([allr_h[r, : int(counts[r])] for r in range(world)], axis=0)
         else:
             merged = chain
             survivors += nsurv
+        if trace:
+            print(f"[pcr dist] wave [{begin}, {end}): wave_fn {(t1 - t0) * 1e3:.2f} ms, exchange {(time.perf_counter() - t1) * 1e3:.2f} ms",
+                  file=sys.stderr)
         recs = array_to_records(merged)
         stop = C.c_int(0)
         lib.pcr_ransac_scan(recs, C.c_int(merged.shape[0]), C.c_int64(begin), C.c_int64(end), C.c_int(n_corr),
@@ -106,7 +127,7 @@ def ransac_distributed(wave_fn, n_corr: int, n_src: int, k_d: int, max_iter: int
         if stop.value:
             break
         if wave < max_wave * world:
-            wave *= 2
+            wave *= WAVE_GROWTH
     state.survivors = survivors
     if state.hyp_evaluated > max_iter:
         state.hyp_evaluated = max_iter
@@ -141,8 +162,12 @@ def ransac_multi_gpu(eng, src, tgt, corr, max_dist: float, max_iter: int, confid
         st.best_hyp = -1
         st.est_k = max_iter
         return DeviceRegResult.from_c(st), {"waves": 0}
-    state, stats = ransac_distributed(wave_fn, int(corr.shape[0]), int(src.shape[0]), k_d, int(max_iter), confidence,
-                                      group=group, device=eng.tdev, first_wave=first_wave, max_wave=max_wave, lib=eng.lib)
+    eng.ransac_session_begin(src, tgt, max_dist)  # grid + sorted source once, not once per wave
+    try:
+        state, stats = ransac_distributed(wave_fn, int(corr.shape[0]), int(src.shape[0]), k_d, int(max_iter), confidence,
+                                          group=group, device=eng.tdev, first_wave=first_wave, max_wave=max_wave, lib=eng.lib)
+    finally:
+        eng.ransac_session_end()
     return DeviceRegResult.from_c(state), stats
 
 

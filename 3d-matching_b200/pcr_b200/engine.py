@@ -266,6 +266,19 @@ class Engine:
                                                  C.c_int64(best_sum), recs, C.c_int(cap), C.byref(n), C.byref(ns)))
         return recs, n.value, ns.value
 
+    def ransac_session_begin(self, src, tgt, max_dist: float) -> None:
+        """Build the target grid / sorted source once for a series of ransac_wave calls on these clouds."""
+        self._need_xyzw(src, "source")
+        self._need_xyzw(tgt, "target")
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_ransac_session_begin(self.ctx, _ptr(src), C.c_int(src.shape[0]), _ptr(tgt),
+                                                          C.c_int(tgt.shape[0]), C.c_double(max_dist)))
+
+    def ransac_session_end(self) -> None:
+        with self._lock:
+            self._check(self.lib.pcr_ransac_session_end(self.ctx))
+
     def ransac_step(self, src, tgt, corr, seed: int, h_begin: int, count: int) -> torch.Tensor:
         self._need_xyzw(src, "source")
         self._need_xyzw(tgt, "target")

@@ -414,7 +414,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-aux", action="store_true", help="skip the RANSAC hyp/s and 1M-point ICP legs")
-    ap.add_argument("--ransac-hyps", type=int, default=2000000)
+    ap.add_argument("--ransac-hyps", type=int, default=10000000)
     ap.add_argument("--icp-points", type=int, default=1000000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

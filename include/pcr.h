@@ -147,6 +147,13 @@ PCR_API int pcr_ransac_wave(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, con
                             int64_t hyp_end, uint64_t seed, int64_t best_count, int64_t best_sum_d2_fixed,
                             pcr_hyp_record *records_host, int cap, int *n_records_host,
                             int64_t *n_survivors_host);
+/* Optional session around a series of pcr_ransac_wave calls on the SAME clouds: the target search grid and the
+ * spatially sorted source are built once (into buffers owned by the context) instead of once per wave.  The caller
+ * must not modify the two clouds between begin and end; a wave on other buffers / sizes / max_dist simply prepares
+ * its own work as before.  pcr_ransac_session_end (or pcr_destroy) releases the buffers. */
+PCR_API int pcr_ransac_session_begin(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                                     double max_dist);
+PCR_API int pcr_ransac_session_end(pcr_ctx *ctx);
 /* Host-only: replay the sequential loop over records sorted by hypothesis index, updating *state.
  * Returns 1 in *stop_host when the early-exit bound was reached inside [hyp_begin, hyp_end). */
 PCR_API int pcr_ransac_scan(const pcr_hyp_record *records_host, int n, int64_t hyp_begin, int64_t hyp_end, int c,
