@@ -355,7 +355,7 @@ def run_aux(eng, args, world, rank, peaks):
     sf, tf = eng.compute_fpfh(sd, sn, 5 * v, 100), eng.compute_fpfh(td, tn, 5 * v, 100)
     corr = eng.match_features(sf, tf, True).contiguous()
     H = args.ransac_hyps
-    ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, 200000, 1.0, 7)  # warm-up
+    ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, H, 1.0, 7)  # warm-up at full size: the scratch arena grows here, not in the timed call
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
