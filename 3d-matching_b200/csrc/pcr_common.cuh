@@ -209,49 +209,54 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
         const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
         const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
         const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
-        // per-axis squared slab distances (in cells, shrunk by the 1e-4 slack) to the -1 / 0 / +1 neighbour slabs
-        const float ry = fyf - (float)cy, rz = fzf - (float)cz;  // position inside the home cell, [0,1) when inside the grid
-        const float ym = fmaxf(ry - 1e-4f, 0.0f), yp = fmaxf(1.0f - ry - 1e-4f, 0.0f);
-        const float zm = fmaxf(rz - 1e-4f, 0.0f), zp = fmaxf(1.0f - rz - 1e-4f, 0.0f);
-        const float ey2[3] = {ym * ym * h2, 0.0f, yp * yp * h2};
-        const float ez2[3] = {zm * zm * h2, 0.0f, zp * zp * h2};
-        // visiting order: home row first, then the 8 others; (dy+1, dz+1) packed 2 bits each, 9 entries
-        //   o:      0      1      2      3      4      5      6      7      8
-        //   dy+1:   1      0      0      0      1      1      2      2      2
-        //   dz+1:   1      0      1      2      0      2      0      1      2
-        const uint32_t DYP = 1u | (0u << 2) | (0u << 4) | (0u << 6) | (1u << 8) | (1u << 10) | (2u << 12) | (2u << 14) | (2u << 16);
-        const uint32_t DZP = 1u | (0u << 2) | (1u << 4) | (2u << 6) | (0u << 8) | (2u << 10) | (0u << 12) | (1u << 14) | (2u << 16);
-        const bool inside = (cy >= 0 && cy < g.ny && cz >= 0 && cz < g.nz);
-#pragma unroll 1
-        for (int o = 0; o < 9; o++) {
-            const int iy = (DYP >> (2 * o)) & 3, iz = (DZP >> (2 * o)) & 3;
-            const int y = cy + iy - 1, z = cz + iz - 1;
-            if (y < y0 || y > y1 || z < z0 || z > z1) continue;
+        // home row first: it usually holds the nearest point
+        if (cy >= y0 && cy <= y1 && cz >= z0 && cz <= z1) {
             const float best = __uint_as_float((uint32_t)(bkey >> 32));
-            if (o > 0) {
-                float lb;
-                if (inside) {
-                    lb = (iy == 0 ? ey2[0] : (iy == 1 ? 0.0f : ey2[2])) + (iz == 0 ? ez2[0] : (iz == 1 ? 0.0f : ez2[2]));
-                } else {  // query outside the grid: general slab distance
+            const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
+            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
+            if (xa <= xb) {
+                const long long row = ((long long)cz * g.ny + cy) * g.nx;
+                const uint32_t b = __ldg(g.start + row + xa);
+                const uint32_t e = __ldg(g.start + row + xb + 1);
+                for (uint32_t k = b; k < e; k++) {
+                    const float4 p = __ldg(g.sorted + k);
+                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                    bkey = key < bkey ? key : bkey;
+                }
+            }
+        }
+        // then only the rows inside the window that the current best distance reaches in y and z (typically 1-3 of the
+        // 8): rows outside it have a slab distance above the best, exactly the rows the per-row test would skip
+        {
+            const float best0 = __uint_as_float((uint32_t)(bkey >> 32));
+            const float rw = sqrtf(best0) * inv_hf * 1.0001f + 1e-4f;
+            const int ya = max(y0, (int)floorf(fyf - rw)), yb = min(y1, (int)floorf(fyf + rw));
+            const int za = max(z0, (int)floorf(fzf - rw)), zb = min(z1, (int)floorf(fzf + rw));
+#pragma unroll 1
+            for (int z = za; z <= zb; z++) {
+#pragma unroll 1
+                for (int y = ya; y <= yb; y++) {
+                    if (y == cy && z == cz) continue;
+                    const float best = __uint_as_float((uint32_t)(bkey >> 32));
                     const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
                     const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
                     const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
-                    lb = (sy * sy + sz * sz) * h2;
+                    if ((sy * sy + sz * sz) * h2 > best) continue;
+                    // cells of the row that can hold a point within the current best distance (in cell units, padded)
+                    const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
+                    const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
+                    if (xa > xb) continue;
+                    const long long row = ((long long)z * g.ny + y) * g.nx;
+                    const uint32_t b = __ldg(g.start + row + xa);
+                    const uint32_t e = __ldg(g.start + row + xb + 1);
+                    for (uint32_t k = b; k < e; k++) {
+                        const float4 p = __ldg(g.sorted + k);
+                        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                        const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+                        bkey = key < bkey ? key : bkey;
+                    }
                 }
-                if (lb > best) continue;
-            }
-            // cells of the row that can hold a point within the current best distance (in cell units, padded)
-            const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
-            const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
-            if (xa > xb) continue;
-            const long long row = ((long long)z * g.ny + y) * g.nx;
-            const uint32_t b = __ldg(g.start + row + xa);
-            const uint32_t e = __ldg(g.start + row + xb + 1);
-            for (uint32_t k = b; k < e; k++) {
-                const float4 p = __ldg(g.sorted + k);
-                const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
-                bkey = key < bkey ? key : bkey;
             }
         }
     }
