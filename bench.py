@@ -267,6 +267,7 @@ def run_engine(args):
             ach = st["bytes"] / (st["ms"] * 1e-3) / 1e9
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": None}
+        roof["traffic"], roof["traffic_source"] = ncu_traffic(name)
         roof.update({"avg_launch_us": per_launch_ms * 1e3, "launches_per_step": st["launches"] / args.steps,
                      "share_of_step": st["ms"] / step_total, "peak_source": peaks["source"],
                      "algorithmic_bytes_per_launch": st["bytes"] / max(st["launches"], 1)})
@@ -332,6 +333,19 @@ def run_engine(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed ncu --set full
+    capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None when the class was not captured."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        e = t["kernels"].get(kernel_class)
+        return (e["dram_bytes_per_launch"], f"profiles/r1_traffic.json ({t['source']})") if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
 
 
 def ctypes_sizeof_result():
