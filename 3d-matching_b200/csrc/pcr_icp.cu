@@ -145,7 +145,11 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
     L->pass = pass + 1;
 }
 
-constexpr int ICP_THREADS = 256;
+#ifndef PCR_ICP_THREADS
+#define PCR_ICP_THREADS 256
+#endif
+constexpr int ICP_THREADS = PCR_ICP_THREADS;  // a multiple of 128 (the accumulate phase works on groups of 4 warps x 128 rows)
+constexpr int ICP_CTAS_PER_SM = 768 / ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 
 // Result of the correspondence step for one source point: target index (-1: none), fp32 squared distance, and the
@@ -293,7 +297,7 @@ __device__ __forceinline__ void icp_grid_barrier(unsigned int *bar, unsigned int
 //
 // End of pass: one 64-bit atomic per CTA and sum into a triple-buffered accumulator, ONE grid barrier, then every
 // CTA solves the 6x6 system redundantly (bit-identical), so no second barrier / broadcast is needed.
-__global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__restrict__ src, int ns, Grid g,
+__global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(const float4 *__restrict__ src, int ns, Grid g,
                                                                 const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
                                                                 float r2, IcpState *__restrict__ S, float4 *__restrict__ st0,
                                                                 float4 *__restrict__ st1, float4 *__restrict__ st2,
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__
     const int max_iter = S->max_iter;
     const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
     const int grp = warp & 3;                       // entry group of this warp
-    const int row0 = (warp >> 2) * (ICP_THREADS / 2) + lane;  // rows row0 + 32 k, k = 0..3
+    const int row0 = (warp >> 2) * 128 + lane;      // rows row0 + 32 k, k = 0..3 (each group of 4 warps owns 128 rows)
     __syncthreads();
 
     for (int pass = 0;; pass++) {
@@ -408,7 +412,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 3) k_icp_persist(const float4 *__
             else { gr = -1; sl = e - 20; }                       // 27: count (slot 7), 28: sum d2 (slot 8), all warps
             long long sum = 0;
             if (gr >= 0) {
-                sum = red[gr][sl] + red[gr + 4][sl];
+#pragma unroll
+                for (int w = gr; w < ICP_WARPS; w += 4) sum += red[w][sl];
             } else {
 #pragma unroll
                 for (int w = 0; w < ICP_WARPS; w++) sum += red[w][sl];

@@ -146,3 +146,37 @@ def test_icp_1m_properties(eng):
     assert float(d.max()) < 0.4 * v * (1 + 1e-6)
     assert abs(g.inlier_rmse - float(torch.sqrt((d2[corr >= 0].double()).mean()))) < 1e-9
     assert np.abs(g.transformation - T).max() < 5e-5
+
+
+def test_benchmark_cli_report_and_export(tmp_path, eng):
+    """The benchmark_ransac.py counterpart: same phases and report table as the reference's harness
+    (benchmark_ransac.py:223-280, src/utils/profiler.py:151-215), plus the headless export."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("b200_benchmark_ransac", os.path.join(root, "3d-matching_b200", "benchmark_ransac.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from pcr_b200.plyio import read_ply, write_ply
+    v = 0.005
+    src, tgt, T_true = synth.make_pair(8000, v, 4242)
+    write_ply(tmp_path / "sample.ply", src)
+    write_ply(tmp_path / "target.ply", tgt)
+    prof, res = mod.run_comprehensive_benchmark(tmp_path / "sample.ply", tmp_path / "target.ply", v, 0.5, 20, 20000, icp=True,
+                                                export_dir=tmp_path / "out", report_path=tmp_path / "benchmark_results.txt",
+                                                quiet=True)
+    report = (tmp_path / "benchmark_results.txt").read_text()
+    assert "PROFILING REPORT" in report and "Median (ms)" in report and "TOTAL" in report
+    for name in ("ply_loading", "correspondence_computation", "ransac_iteration", "compute_transformation",
+                 "evaluate_inliers", "full_ransac", "icp_refinement"):
+        assert name in report
+    st = prof.stats()
+    assert len(st["ransac_iteration"]) == 20 and len(st["full_ransac"]) == 1
+    out = json.loads((tmp_path / "out" / "registration.json").read_text())
+    T = np.array(out["icp"]["transformation"])
+    assert np.abs(T[:3, :3] - T_true[:3, :3]).max() < 5e-3 and out["icp"]["fitness"] > 0.9
+    aligned, _ = read_ply(tmp_path / "out" / "source_aligned.ply")
+    assert aligned.shape == src.shape
+    # the exported cloud is the source moved by the exported transform
+    assert np.abs(aligned - (src.astype(np.float64) @ T[:3, :3].T + T[:3, 3])).max() < 1e-5

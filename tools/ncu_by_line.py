@@ -8,6 +8,7 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", SO], cwd=tmp, capture_output=True)
 cubins = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")]
 lines_of = None
+cands = []  # every function whose section name contains kname: (instruction -> source line) lists
 for cb in cubins:
     dis = subprocess.run(["nvdisasm", "-g", "-c", cb], capture_output=True, text=True).stdout
     if kname not in dis:
@@ -16,6 +17,9 @@ for cb in cubins:
     for ln in dis.splitlines():
         m = re.match(r"\s*\.text\.(\S+):", ln)
         if m:
+            if seq:
+                cands.append(seq)
+            seq = []
             infn = kname in m.group(1)
             continue
         if not infn:
@@ -27,8 +31,7 @@ for cb in cubins:
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             seq.append(cur)
     if seq:
-        lines_of = seq
-        break
+        cands.append(seq)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", kid, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r)
@@ -41,7 +44,13 @@ for r in rows[hi + 1:]:
         body.append(r)
 ie, ss = h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
 f = lambda x: float(x) if x.replace(".", "", 1).isdigit() else 0.0
-print(f"sass lines: ncu {len(body)} nvdisasm {len(lines_of) if lines_of else None}")
+# template instantiations share a name: take the one with the same number of SASS instructions as the profile
+for c in cands:
+    if len(c) == len(body):
+        lines_of = c
+if lines_of is None and cands:
+    lines_of = min(cands, key=lambda c: abs(len(c) - len(body)))
+print(f"sass lines: ncu {len(body)} nvdisasm {len(lines_of) if lines_of else None} (of {[len(c) for c in cands]})")
 agg = collections.defaultdict(lambda: [0.0, 0.0])
 for i, r in enumerate(body):
     key = lines_of[i] if lines_of and i < len(lines_of) else ("?", 0)
