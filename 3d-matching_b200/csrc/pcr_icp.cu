@@ -93,7 +93,10 @@ struct IcpLocal {
     int pass, done, iterations, converged;
 };
 
-// end-of-pass logic (ONE thread per CTA): convergence test, 6x6 solve, Euler-ZYX update, T <- U T
+// end-of-pass logic (ONE thread per CTA): convergence test, 6x6 solve, Euler-ZYX update, T <- U T.
+// ~6,000 cycles per pass.  It is a latency chain (six pivots, each behind an fp64 division, then two substitutions and
+// the sin/cos polynomials), not an instruction-count problem: a warp-parallel version (row i of the factorisation on
+// lane i, the three sin/cos pairs on three lanes, U T on twelve) was measured at 7,400 cycles and dropped.
 // fA / fb: the normal equations A x = b already converted to fp64 (shared memory, filled by 27 threads)
 __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, const double (*fA)[6], const double *fb,
                                              double isc_d, double rel_fit, double rel_rmse, int max_iter, int ns) {
