@@ -141,6 +141,9 @@ PCR_API int pcr_ransac(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const fl
  * range — a superset: every survivor better than the running best (best_count, best_sum_d2_fixed; pass 0,0
  * at the start), sorted by hypothesis index — to records_host (capacity cap; PCR_ERR_INVALID if it does not
  * fit); *n_records_host = how many; *n_survivors_host = survivors in the range.
+ * Which non-maximal survivors the superset also holds depends on kernel timing (survivors prune against the completed
+ * evaluations of earlier hypotheses of the same wave); the prefix maxima themselves, and therefore everything
+ * pcr_ransac_scan derives, are deterministic.
  * Used by the multi-GPU driver: each rank scores its slice, records are all-gathered, pcr_ransac_scan merges. */
 PCR_API int pcr_ransac_wave(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
                             const int *corr_dev, int c, double max_dist, double edge_sim, int64_t hyp_begin,

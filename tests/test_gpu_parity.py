@@ -175,6 +175,33 @@ def test_ransac_waves_match_single_call(orc, eng, pair):
     assert np.array_equal(np.array(st.transformation).reshape(4, 4), o.transformation)
 
 
+def test_ransac_session_and_multi_gpu_driver(orc, eng, pair):
+    """ransac_multi_gpu (world 1: the same wave loop the ranks run, inside a pcr_ransac_session) equals the oracle's
+    sequential loop; waves inside and outside a session return the same records; a wave on other buffers while a
+    session is open prepares its own work."""
+    from pcr_b200.dist import prefix_maxima, ransac_multi_gpu, records_to_array
+    v = pair["v"]
+
+    def chain(w):  # a wave returns a SUPERSET of its prefix maxima (which extras it holds depends on timing); the chain is exact
+        return prefix_maxima(records_to_array(w[0], w[1]), 0, 0)
+    for conf, iters, seed in ((0.999, 60000, 5), (1.0, 9000, 11)):
+        r, stats = ransac_multi_gpu(eng, pair["sd"], pair["td"], pair["corr"], 1.5 * v, iters, conf, seed, first_wave=512)
+        o = orc.ransac(pair["osd"], pair["otd"], pair["ocorr"], 1.5 * v, iters, conf, seed)
+        assert (r.best_hyp, r.inlier_count, r.sum_d2_fixed, r.hyp_evaluated) == (o.best_hyp, o.inlier_count, o.sum_d2_fixed, o.hyp_evaluated)
+        assert np.array_equal(r.transformation, o.transformation)
+        assert stats["waves"] >= (3 if conf == 1.0 else 1)  # confidence 1.0 never exits early: 512, 1024, 2048, ...
+    plain = eng.ransac_wave(pair["sd"], pair["td"], pair["corr"], 1.5 * v, 0, 3000, 5)
+    eng.ransac_session_begin(pair["sd"], pair["td"], 1.5 * v)
+    try:
+        inside = eng.ransac_wave(pair["sd"], pair["td"], pair["corr"], 1.5 * v, 0, 3000, 5)
+        other = eng.ransac_wave(pair["td"], pair["sd"], pair["corr"][:, [1, 0]].contiguous(), 1.5 * v, 0, 3000, 5)  # not the session's clouds
+    finally:
+        eng.ransac_session_end()
+    assert plain[2] == inside[2] and np.array_equal(chain(plain), chain(inside))
+    after = eng.ransac_wave(pair["td"], pair["sd"], pair["corr"][:, [1, 0]].contiguous(), 1.5 * v, 0, 3000, 5)
+    assert other[2] == after[2] and np.array_equal(chain(other), chain(after)) and len(chain(plain)) >= 1
+
+
 def test_ransac_degenerate(eng, pair):
     v = pair["v"]
     r = eng.ransac(pair["sd"], pair["td"], pair["corr"][:2].contiguous(), 1.5 * v, 100)
