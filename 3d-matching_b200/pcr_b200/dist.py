@@ -171,10 +171,14 @@ def ransac_multi_gpu(eng, src, tgt, corr, max_dist: float, max_iter: int, confid
     return DeviceRegResult.from_c(state), stats
 
 
-def align_batch(eng, pairs, params, group=None):
+def align_batch(eng, pairs, params, group=None, workers: int = 1):
     """Batch of independent pairs sharded pair i -> rank i mod world.  `pairs` is a sequence of (src, tgt) packed
     CUDA tensors or a callable i -> (src, tgt) plus its length as (fn, n).  Returns an (n, 18) float64 array on
-    every rank: 16 transform entries, fitness, inlier RMSE."""
+    every rank: 16 transform entries, fitness, inlier RMSE.
+
+    workers > 1: the rank's pairs are aligned by that many host threads, each with its own engine context and CUDA
+    stream, so that the host synchronisations of one alignment (voxel counts, RANSAC waves) overlap with the kernels
+    of another; the result of a pair does not depend on it."""
     if isinstance(pairs, tuple) and callable(pairs[0]):
         fn, n = pairs
     else:
@@ -183,12 +187,41 @@ def align_batch(eng, pairs, params, group=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     per = (n + world - 1) // world
     out = torch.zeros((per, 18), dtype=torch.float64)
-    for k, i in enumerate(range(rank, n, world)):
+    mine_idx = list(range(rank, n, world))
+
+    def run(e, k, i):
         s, t = fn(i)
-        r = eng.align_device(s, t, params)
+        r = e.align_device(s, t, params)
         out[k, :16] = torch.tensor(list(r.icp.transformation), dtype=torch.float64)
         out[k, 16] = r.icp.fitness
         out[k, 17] = r.icp.inlier_rmse
+
+    if workers <= 1 or len(mine_idx) <= 1:
+        for k, i in enumerate(mine_idx):
+            run(eng, k, i)
+    else:
+        import threading
+        from .engine import Engine
+        pool = _worker_engines(eng, workers, Engine)
+        errors = []
+
+        def work(w):
+            try:
+                torch.cuda.set_device(eng.tdev)
+                with torch.cuda.stream(pool[w][1]):
+                    for k in range(w, len(mine_idx), workers):
+                        run(pool[w][0], k, mine_idx[k])
+                    pool[w][1].synchronize()
+            except Exception as exc:  # surfaced on the calling thread
+                errors.append(exc)
+        torch.cuda.current_stream(eng.tdev).synchronize()  # inputs produced on the caller's stream are complete
+        threads = [threading.Thread(target=work, args=(w,)) for w in range(workers)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
     if world > 1:
         mine = out.reshape(-1).to(eng.tdev)
         allr = torch.empty((world * per * 18,), dtype=torch.float64, device=eng.tdev)
@@ -200,3 +233,17 @@ def align_batch(eng, pairs, params, group=None):
             res[idx] = allr[r, : len(idx)]
         return res.numpy()
     return out[:n].numpy()
+
+
+_worker_pool: dict = {}
+
+
+def _worker_engines(eng, workers: int, Engine):
+    """(engine, stream) per worker thread, created once per device: worker 0 reuses the caller's engine."""
+    key = (eng.tdev.index, workers)
+    if key not in _worker_pool:
+        pool = [(eng, torch.cuda.Stream(device=eng.tdev))]
+        for _ in range(workers - 1):
+            pool.append((Engine(eng.tdev.index), torch.cuda.Stream(device=eng.tdev)))
+        _worker_pool[key] = pool
+    return _worker_pool[key]

@@ -386,6 +386,39 @@ def run_aux(eng, args, world, rank, peaks):
     out["ransac"] = {"hypotheses": H, "ms": ms, "hyp_per_s": H / (ms * 1e-3), "survivors": r.survivors,
                      "checker_pass_rate": r.survivors / H, "best_hyp": r.best_hyp, "inlier_count": r.inlier_count,
                      "waves": st["waves"], "n_gpus": world}
+    # batch of independent pairs (config 5 style: 50k-point pairs, full pipeline, reference-default criteria), pair i ->
+    # rank i mod world, no communication until the final all-gather of 18 doubles per pair
+    from pcr_b200.dist import align_batch
+    B = args.batch_pairs
+    if B > 0:
+        pairs = []
+        for i in range(B * world):
+            if i % world == rank:
+                s_i, t_i, _ = synth.make_pair(50000, v, 30000 + i)
+                pairs.append((eng.pack(s_i), eng.pack(t_i)))
+            else:
+                pairs.append(None)
+        pb = eng.default_params(v)
+        pb.ransac_max_iter = RANSAC_ITERS
+        pb.seed = 7
+        batch = {"pairs": B * world, "points_per_cloud": 50000, "criteria": "confidence 0.999, ICP 30 iterations / 1e-6"}
+        for workers in (1, 3):
+            align_batch(eng, pairs, pb, workers=workers)  # warm-up (worker contexts, arenas)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tab = align_batch(eng, pairs, pb, workers=workers)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=eng.tdev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            batch[f"pairs_per_s_workers{workers}"] = B * world / dt
+            batch[f"min_fitness_workers{workers}"] = float(tab[:, 16].min())
+        out["batch"] = batch
+        del pairs
     # ICP at 1M points: replicas only (single-pair ICP does not shard); aggregate = world x per-GPU rate
     n = args.icp_points
     s1, t1, _ = synth.make_icp_pair(n, v, 20243)
@@ -430,6 +463,7 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the RANSAC hyp/s and 1M-point ICP legs")
     ap.add_argument("--ransac-hyps", type=int, default=10000000)
     ap.add_argument("--icp-points", type=int, default=1000000)
+    ap.add_argument("--batch-pairs", type=int, default=8, help="pairs per GPU of the batch leg (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -180,3 +180,22 @@ def test_benchmark_cli_report_and_export(tmp_path, eng):
     assert aligned.shape == src.shape
     # the exported cloud is the source moved by the exported transform
     assert np.abs(aligned - (src.astype(np.float64) @ T[:3, :3].T + T[:3, 3])).max() < 1e-5
+
+
+def test_align_batch_workers_match_sequential(eng):
+    """Batch of independent pairs: concurrent worker threads (own context + stream each) give the same
+    table as the sequential loop, and each row equals a single align of that pair."""
+    from pcr_b200.dist import align_batch
+    v = 0.005
+    clouds = [synth.make_pair(6000, v, 500 + i) for i in range(5)]
+    pairs = [(eng.pack(s), eng.pack(t)) for s, t, _ in clouds]
+    p = eng.default_params(v)
+    p.ransac_max_iter = 20000
+    p.seed = 3
+    seq = align_batch(eng, pairs, p, workers=1)
+    par = align_batch(eng, pairs, p, workers=3)
+    assert seq.shape == (5, 18) and np.array_equal(seq, par)
+    one = eng.align_device(pairs[2][0], pairs[2][1], p)
+    assert np.array_equal(seq[2, :16], np.array(one.icp.transformation)) and seq[2, 16] == one.icp.fitness
+    for i, (_, _, T) in enumerate(clouds):
+        assert np.abs(seq[i, :16].reshape(4, 4)[:3, :3] - T[:3, :3]).max() < 5e-3 and seq[i, 16] > 0.9
