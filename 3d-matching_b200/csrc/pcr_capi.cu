@@ -1,4 +1,6 @@
 // pcr_capi.cu — extern "C" entry points declared in include/pcr.h and the end-to-end align driver.
+#include <cstdlib>
+
 #include "pcr_common.cuh"
 
 typedef unsigned long long u64;
@@ -196,46 +198,98 @@ struct StageTimer {
     }
 };
 
+int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out);
+
+// Ply._preprocess of one cloud (src/ply/ply.py:106-120) on `c`: voxel grid, normals, FPFH
+static int preprocess_cloud(pcr_ctx *c, const float4 *pts, int n, double v, float4 **down, int *m, float4 **nrm, float **fpfh) {
+    pcr_ctx *ctx = c;
+    PCR_ALLOC(d, float4, (size_t)n);
+    PCR_TRY(pcr_voxel_impl(ctx, pts, n, v, d, m));
+    PCR_ALLOC(nn, float4, (size_t)*m);
+    PCR_TRY(pcr_normals_impl(ctx, d, *m, 2.0 * v, 30, nn));
+    PCR_ALLOC(f, float, (size_t)*m * 33);
+    PCR_TRY(pcr_fpfh_impl(ctx, d, nn, *m, 5.0 * v, 100, f));
+    *down = d;
+    *nrm = nn;
+    *fpfh = f;
+    return PCR_OK;
+}
+
+// The full-resolution normals (needed only by ICP) run on the helper context (own stream + host thread) NEXT TO matching
+// and RANSAC, whose validation kernels leave issue slots free:
+//   preprocessing of both clouds (main)  ->  matching + RANSAC (main) || full-resolution normals (helper)  ->  ICP (main)
+// Every stage computes exactly what it computes alone, so results do not depend on the overlap (PCR_ALIGN_OVERLAP=0
+// runs the stages one after the other on the main context).  stage_ms are the main thread's stage times: 0 voxel +
+// normals + FPFH of both clouds, 3 matching, 4 RANSAC, 5 waiting for the full-resolution normals, 6 ICP, 7 total.
 static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, const pcr_align_params *p,
                         pcr_align_result *res) {
     memset(res, 0, sizeof(*res));
     const double v = p->voxel_size;
     if (!(v > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "voxel_size must be > 0");
     if (ns <= 0 || nt <= 0) return pcr_fail(ctx, PCR_ERR_INVALID, "Point cloud is empty");  // src/ply/ply.py:81-84
+    static const bool overlap = !(getenv("PCR_ALIGN_OVERLAP") && atoi(getenv("PCR_ALIGN_OVERLAP")) == 0);
     StageTimer tm(ctx->stream);
     tm.mark();
-    // Ply._preprocess for both clouds (src/ply/ply.py:106-120)
-    PCR_ALLOC(sd, float4, (size_t)ns);
-    PCR_ALLOC(td, float4, (size_t)nt);
+    float4 *sd = nullptr, *td = nullptr, *sn = nullptr, *tn = nullptr, *tfn = nullptr;
+    float *sf = nullptr, *tf = nullptr;
     int ms = 0, mt = 0;
-    PCR_TRY(pcr_voxel_impl(ctx, src, ns, v, sd, &ms));
-    PCR_TRY(pcr_voxel_impl(ctx, tgt, nt, v, td, &mt));
-    tm.mark();
-    PCR_ALLOC(sn, float4, (size_t)ms);
-    PCR_ALLOC(tn, float4, (size_t)mt);
-    PCR_TRY(pcr_normals_impl(ctx, sd, ms, 2.0 * v, 30, sn));
-    PCR_TRY(pcr_normals_impl(ctx, td, mt, 2.0 * v, 30, tn));
-    tm.mark();
-    PCR_ALLOC(sf, float, (size_t)ms * 33);
-    PCR_ALLOC(tf, float, (size_t)mt * 33);
-    PCR_TRY(pcr_fpfh_impl(ctx, sd, sn, ms, 5.0 * v, 100, sf));
-    PCR_TRY(pcr_fpfh_impl(ctx, td, tn, mt, 5.0 * v, 100, tf));
-    tm.mark();
-    // global_registration (src/matcher/ransac.py:41-59): mutual filter True, threshold 1.5 v
-    PCR_ALLOC(corr, int, 2 * (size_t)ms);
-    int c = 0;
-    PCR_TRY(pcr_match_impl(ctx, sf, ms, tf, mt, 1, 0.1, corr, &c));
-    tm.mark();
-    PCR_TRY(pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed,
-                            &res->ransac));
-    tm.mark();
-    // Ply._add_normals on the full-resolution clouds (src/ply/ply.py:65,133-135)
-    PCR_ALLOC(tfn, float4, (size_t)nt);
-    PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, tfn));
-    if (p->source_normals) {
-        PCR_ALLOC(sfn, float4, (size_t)ns);
-        PCR_TRY(pcr_normals_impl(ctx, src, ns, 2.0 * v, 30, sfn));
+    pcr_ctx *h = nullptr;
+    cudaEvent_t ready = nullptr;
+    if (overlap) {
+        PCR_TRY(pcr_helper_get(ctx, &h));
+        // the clouds were produced on the main stream: the helper stream waits for them
+        PCR_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(ready, ctx->stream));
+        PCR_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
+        pcr_arena_reset(h);
+        h->bounds_cache.clear();
     }
+    // (Preprocessing the two clouds concurrently was measured and gains nothing: each of its kernels fills the GPU.)
+    int rc = preprocess_cloud(ctx, src, ns, v, &sd, &ms, &sn, &sf);
+    if (rc == PCR_OK) rc = preprocess_cloud(ctx, tgt, nt, v, &td, &mt, &tn, &tf);
+    if (rc != PCR_OK) {
+        if (ready) cudaEventDestroy(ready);
+        return rc;
+    }
+    tm.mark();
+    tm.mark();
+    tm.mark();
+    // Ply._add_normals on the full-resolution clouds (src/ply/ply.py:65,133-135): next to matching + RANSAC
+    auto full_normals = [=, &tfn](pcr_ctx *c) -> int {
+        pcr_ctx *ctx = c;
+        PCR_ALLOC(t, float4, (size_t)nt);
+        PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, t));
+        tfn = t;
+        if (p->source_normals) {
+            PCR_ALLOC(sfn, float4, (size_t)ns);
+            PCR_TRY(pcr_normals_impl(ctx, src, ns, 2.0 * v, 30, sfn));
+        }
+        return PCR_OK;
+    };
+    if (overlap) {
+        ctx->worker->submit([=]() -> int {
+            cudaSetDevice(h->device);
+            const int r = full_normals(h);
+            if (r != PCR_OK) return r;
+            return cudaStreamSynchronize(h->stream) == cudaSuccess ? PCR_OK : PCR_ERR_CUDA;
+        });
+    }
+    // global_registration (src/matcher/ransac.py:41-59): mutual filter True, threshold 1.5 v
+    int c = 0;
+    int *corr = arena<int>(ctx, 2 * (size_t)ms);
+    rc = corr ? pcr_match_impl(ctx, sf, ms, tf, mt, 1, 0.1, corr, &c) : PCR_ERR_OOM;
+    tm.mark();
+    if (rc == PCR_OK)
+        rc = pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed, &res->ransac);
+    tm.mark();
+    if (overlap) {
+        const int rch = ctx->worker->wait();
+        if (rc == PCR_OK && rch != PCR_OK) rc = pcr_fail(ctx, rch, "full-resolution normals: %s", h->err.c_str());
+    } else if (rc == PCR_OK) {
+        rc = full_normals(ctx);
+    }
+    if (ready) cudaEventDestroy(ready);
+    if (rc != PCR_OK) return rc;
     tm.mark();
     // refine_registration (src/matcher/icp.py:41-48): full-resolution clouds, threshold 0.4 v
     PCR_TRY(pcr_icp_impl(ctx, src, ns, tgt, tfn, nt, 0.4 * v, res->ransac.transformation, p->icp_max_iter,

@@ -8,7 +8,11 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pcr.h"
@@ -86,6 +90,26 @@ struct pcr_ctx {
         void *bufs[3] = {nullptr, nullptr, nullptr};  // grid.sorted, grid.start, src_sorted (grow-only, freed at destroy)
         size_t cap[3] = {0, 0, 0};
     } rsess;
+    // pcr_align overlaps independent stages (the two clouds' preprocessing; full-resolution normals next to RANSAC) on
+    // a second context with its own stream, arena and pinned page, driven by one persistent host thread (the stages
+    // contain host synchronisations, so a second stream alone would not overlap them)
+    pcr_ctx *helper = nullptr;
+    struct Worker *worker = nullptr;
+    bool owns_stream = false;
+};
+
+// one persistent host thread executing one task at a time
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> task;
+    bool has_task = false, done = true, quit = false;
+    int rc = 0;
+    Worker();
+    ~Worker();
+    void submit(std::function<int()> f);  // returns immediately
+    int wait();                           // joins the task, returns its status
 };
 
 extern std::atomic<long long> g_pcr_launches;

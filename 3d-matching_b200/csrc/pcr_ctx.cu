@@ -103,6 +103,64 @@ void *pcr_arena_alloc(pcr_ctx *ctx, size_t bytes) {
     return p;
 }
 
+// ---- worker thread ------------------------------------------------------------------------------------
+Worker::Worker() {
+    th = std::thread([this] {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [this] { return has_task || quit; });
+            if (quit) return;
+            std::function<int()> f = std::move(task);
+            has_task = false;
+            lk.unlock();
+            const int r = f();
+            lk.lock();
+            rc = r;
+            done = true;
+            cv.notify_all();
+        }
+    });
+}
+Worker::~Worker() {
+    {
+        std::lock_guard<std::mutex> lk(m);
+        quit = true;
+    }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+}
+void Worker::submit(std::function<int()> f) {
+    std::lock_guard<std::mutex> lk(m);
+    task = std::move(f);
+    has_task = true;
+    done = false;
+    cv.notify_all();
+}
+int Worker::wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this] { return done; });
+    return rc;
+}
+
+// helper context of `ctx` (created on first use): same device, own non-blocking stream
+int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
+    if (!ctx->helper) {
+        pcr_ctx *h = nullptr;
+        const int rc = pcr_create(ctx->device, &h);
+        if (rc != PCR_OK) return pcr_fail(ctx, rc, "cannot create the helper context");
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            pcr_destroy(h);
+            return pcr_fail(ctx, PCR_ERR_CUDA, "cannot create the helper stream");
+        }
+        h->owns_stream = true;
+        ctx->helper = h;
+        ctx->worker = new Worker();
+    }
+    ctx->helper->profiling = ctx->profiling;
+    *out = ctx->helper;
+    return PCR_OK;
+}
+
 extern "C" {
 
 int pcr_version(void) { return 100; }
@@ -136,6 +194,11 @@ int pcr_create(int device, pcr_ctx **out) {
 int pcr_destroy(pcr_ctx *ctx) {
     if (!ctx) return PCR_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->worker) {
+        ctx->worker->wait();
+        delete ctx->worker;
+    }
+    if (ctx->helper) pcr_destroy(ctx->helper);
     cudaStreamSynchronize(ctx->stream);
     for (void *b : ctx->blocks) cudaFree(b);
     for (void *b : ctx->rsess.bufs)
@@ -143,6 +206,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCR_OK;
 }
@@ -191,6 +255,24 @@ int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset) {
         ctx->ev_pool.push_back(p.b);
     }
     ctx->pending.clear();
+    if (ctx->helper) {  // kernels that pcr_align ran on the helper context count for this context
+        pcr_ctx *h = ctx->helper;
+        cudaStreamSynchronize(h->stream);
+        for (const KPending &p : h->pending) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+                ctx->k_ms[p.id] += ms;
+                ctx->k_launches[p.id] += p.launches;
+                ctx->k_bytes[p.id] += p.bytes * (double)p.launches;
+                ctx->k_flops[p.id] += p.flops * (double)p.launches;
+            } else {
+                cudaGetLastError();
+            }
+            h->ev_pool.push_back(p.a);
+            h->ev_pool.push_back(p.b);
+        }
+        h->pending.clear();
+    }
     for (int i = 0; i < KC_COUNT; i++) {
         out[i].total_ms = ctx->k_ms[i];
         out[i].launches = ctx->k_launches[i];

@@ -302,7 +302,8 @@ def run_engine(args):
     aux = {"align_ms_reference_default_criteria_e2e": ms_default,
            "align_ms_device_resident_no_profiling_events": ms_dev_np,
            "stage_ms_device": {k: float(v) for k, v in zip(
-               ["voxel", "normals_down", "fpfh", "match", "ransac", "normals_full", "icp", "total"], res.stage_ms)},
+               ["preprocess_both_clouds", "_unused1", "_unused2", "match", "ransac",
+                "wait_for_full_res_normals_overlapped_with_ransac", "icp", "total"], res.stage_ms) if not k.startswith("_")},
            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
            "icp_pass_roofline_100k": icp_roof}
     if not args.no_aux:
