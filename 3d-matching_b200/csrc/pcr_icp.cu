@@ -1,15 +1,12 @@
 // pcr_icp.cu — point-to-plane ICP (K9 + K10 + K11 fused), replaces open3d registration_icp as called from
 // src/matcher/icp.py:42-48.
 //
-// Two kernel launches per NN pass, no host synchronisation between passes:
-//   k_icp_nn    — every (Morton-ordered) source point is transformed by the cumulative fp64 transform (D7) and its
-//                 radius-limited nearest target point is found in the uniform grid.  The search is a chain of
-//                 dependent loads (cell range -> candidates), i.e. memory-latency bound, so this kernel is kept
-//                 lean (few registers, maximum occupancy) to keep many loads in flight.
-//   k_icp_accum — the point-to-plane normal equations (21 + 6 sums), the inlier count and the sum of squared
-//                 distances are accumulated as int64 fixed point (D5: order-free, so warp shuffles and atomics
-//                 give bit-reproducible sums); the last block to finish solves the 6x6 system (LDL^T), composes
-//                 the Euler-ZYX update, applies the convergence test and publishes the next transform.
+// ONE persistent cooperative kernel (k_icp_persist) runs the whole loop: per pass, every (Morton-ordered) source point
+// is transformed by the cumulative fp64 transform (D7), its radius-limited nearest target point is found (certified
+// reuse of the previous correspondence where provable, else a search in the uniform grid), its point-to-plane row is
+// quantised and accumulated into the 21 + 6 + 2 integer sums (D5: order-free, so shuffles and atomics give
+// bit-reproducible sums); one grid barrier later every CTA solves the 6x6 system (LDL^T), composes the Euler-ZYX
+// update, applies the convergence test and holds the next transform.  No host synchronisation between passes.
 //
 // HBM roofline: 16 B source + 16 B target + 16 B normal + 4 B index = 52 B per point and pass.
 #include <cstdio>
@@ -293,19 +290,16 @@ __device__ __forceinline__ void icp_grid_barrier(unsigned int *bar, unsigned int
 
 // The WHOLE ICP loop in one persistent cooperative kernel (one launch per pcr_icp call, no host round trips).
 //
-// Per pass and source point (Morton order; a thread owns the same points in every pass, so seed[]/cert[] need no
-// inter-CTA coherence): transform by the cumulative fp64 transform (D7), nearest target point in the uniform grid
-// (certified reuse of the previous correspondence where provable, else the full search — identical results), then the
-// point-to-plane row (J, r) in fp64.  Per source point the state is seed[i] = current correspondence (-1: none) and
-// cert[i] = (query position at the last full search, lower bound of the squared distance to every OTHER target point):
-// if dist(q', t_j) + |q' - q_ref| is below that bound (triangle inequality, 2e-5 relative slack >> fp32 rounding),
-// j is still the unique nearest neighbour and d2 = fp32 dist2(q', t_j) is exactly what the search would return.
+// Per pass and source point (Morton order; a thread owns the same points in every pass, so the per-point state needs
+// no inter-CTA coherence): transform by the cumulative fp64 transform (D7), nearest target point (certified reuse of
+// the previous correspondence where provable, else the grid search — identical results, see icp_point_nn), then the
+// point-to-plane row (J, r) in fp64.
 //
 // Normal equations (rule D5): J (6 entries) and r are quantised ONCE per correspondence to kq-bit integers
 // (kq = min(30, (62 - ceil(log2 n)) / 2), scales 2^(kq - e_J), 2^(kq - e_R)); the 21 + 6 sums are sums of exact
 // int32 x int32 -> int64 products, so they are order-free and bit-reproducible, and one product costs ONE
 // IMAD.WIDE instead of DMUL + DMUL + F2I + 64-bit add.  The quantised rows of a 256-point chunk are staged in
-// shared memory (SoA, double-buffered, one __syncthreads per chunk) and the 27 products are split over the warps:
+// shared memory (SoA, double-buffered, one group barrier per chunk) and the 27 products are split over the warps:
 // warp w forms the sums of entry group w & 3 (7 / 6 / 7 / 7 entries) for 4 rows per lane, so a thread carries
 // 7 accumulators (14 registers) instead of 27 (54) — the NN search keeps its occupancy.  The inlier count and
 // the fixed-point sum of d2 stay with the thread that owns the point.
