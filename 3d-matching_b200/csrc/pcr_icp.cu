@@ -30,6 +30,7 @@ struct IcpState {
     double sc_J, sc_R, sc_d;         // 2^(kq - e_J), 2^(kq - e_R), 2^k_d
     double isc_JJ, isc_Jr, isc_d;    // 2^-2(kq - e_J), 2^-((kq - e_J) + (kq - e_R)), 2^-k_d
     double T_out[16];
+    int trace;             // PCR_ICP_TRACE=1: collect the cycle counters below (two extra atomics per CTA and pass)
     long long dbgmax[64];  // per-pass slowest CTA loop
     long long dbgfin[64];  // per-pass slowest CTA finish
     long long dbgp[64];  // per-pass loop cycles of CTA 0 (first 64 passes)
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
     }
     const double scJ = S->sc_J, scR = S->sc_R, scd = S->sc_d;
     const double isc_JJ = S->isc_JJ, isc_Jr = S->isc_Jr, isc_d = S->isc_d, rel_fit = S->rel_fit, rel_rmse = S->rel_rmse;
-    const int max_iter = S->max_iter;
+    const int max_iter = S->max_iter, trace = S->trace;
     const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
     const int grp = warp & 3;                       // entry group of this warp
     const int row0 = (warp >> 2) * 128 + lane;      // rows row0 + 32 k, k = 0..3 (each group of 4 warps owns 128 rows)
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
             if (sum != 0) atomicAdd((unsigned long long *)&gacc[e], (unsigned long long)sum);
         }
         const long long cb = clock64();
-        if (threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgmax[pass], (unsigned long long)(c1 - c0));  // trace
+        if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgmax[pass], (unsigned long long)(c1 - c0));
         icp_grid_barrier(&S->bar, (unsigned int)(pass + 1) * gridDim.x);
         const long long ce = clock64();
         if (threadIdx.x < 29) {
@@ -457,8 +458,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         const long long c2 = clock64();
         if (threadIdx.x == 0) icp_finish_pass(&L, tot, fA, fb, isc_d, rel_fit, rel_rmse, max_iter, ns);
         __syncthreads();
-        if (threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgfin[pass], (unsigned long long)(clock64() - c2));
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgfin[pass], (unsigned long long)(clock64() - c2));
+        if (trace && blockIdx.x == 0 && threadIdx.x == 0) {
             S->dbg[0] += c1 - c0;
             if (pass < 63) S->dbgp[pass] = c1 - c0;
             S->dbg[1] += c2 - c1;
@@ -550,6 +551,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     memset(hS, 0, sizeof(IcpState));
     for (int i = 0; i < 16; i++) hS->T[i] = init[i];
     hS->max_iter = max_iter;
+    hS->trace = getenv("PCR_ICP_TRACE") ? 1 : 0;
     hS->rel_fit = rel_fit;
     hS->rel_rmse = rel_rmse;
     hS->sc_J = ldexp(1.0, s_J); hS->isc_JJ = ldexp(1.0, -2 * s_J);
