@@ -275,6 +275,39 @@ def test_icp_certified_passes_ties_and_drift(orc, eng, pair):
     assert 0.2 < g.fitness < 1.0
 
 
+@pytest.mark.parametrize("ns", [1, 2, 31, 129, 257, 1000])
+def test_icp_small_and_ragged_sizes(orc, eng, pair, ns):
+    """Source sizes around the kernel's granularities (128-row groups, 256-thread CTAs), down to a single point."""
+    v = pair["v"]
+    rng = np.random.default_rng(ns)
+    sub = np.ascontiguousarray(pair["src"][rng.choice(len(pair["src"]), ns, replace=False)])
+    otn = orc.estimate_normals(pair["tgt"], 2 * v, 30)
+    pert = np.eye(4); pert[:3, :3] = synth.euler_zyx(0.003, 0.002, -0.001); pert[:3, 3] = [3e-4, 1e-4, -2e-4]
+    init = pert @ pair["T"]
+    g, corr = eng.icp_point_to_plane(eng.pack(sub), pair["dt"], eng.pack(otn), 0.4 * v, init, 12, 0.0, 0.0)
+    o = orc.icp_point_to_plane(sub, pair["tgt"], otn, 0.4 * v, init, 12, 0.0, 0.0)
+    assert np.array_equal(corr.cpu().numpy(), o.correspondence)
+    assert (g.inlier_count, g.sum_d2_fixed, g.iterations) == (o.inlier_count, o.sum_d2_fixed, o.iterations)
+    assert np.array_equal(g.transformation, o.transformation)
+
+
+@pytest.mark.parametrize("ms", [3, 40, 300, 513])
+def test_ransac_small_and_ragged_source(orc, eng, pair, ms):
+    """RANSAC validation with source clouds around the chunk sizes of the validation kernel (256 / 512 / 1024)."""
+    v = pair["v"]
+    keep = np.sort(np.random.default_rng(ms).choice(len(pair["osd"]), ms, replace=False))
+    remap = -np.ones(len(pair["osd"]), np.int64); remap[keep] = np.arange(ms)
+    corr = pair["ocorr"][np.isin(pair["ocorr"][:, 0], keep)].copy()
+    corr[:, 0] = remap[corr[:, 0]]
+    if len(corr) < 3:
+        pytest.skip("too few correspondences survive the subsampling")
+    sd = np.ascontiguousarray(pair["osd"][keep])
+    r = eng.ransac(eng.pack(sd), pair["td"], torch.as_tensor(corr.astype(np.int32)).to(eng.tdev).contiguous(), 1.5 * v, 20000, 1.0, 9)
+    o = orc.ransac(sd, pair["otd"], corr.astype(np.int32), 1.5 * v, 20000, 1.0, 9)
+    assert (r.best_hyp, r.inlier_count, r.sum_d2_fixed, r.survivors) == (o.best_hyp, o.inlier_count, o.sum_d2_fixed, o.survivors)
+    assert np.array_equal(r.transformation, o.transformation)
+
+
 def test_icp_edge_cases(eng, pair):
     v = pair["v"]
     n = eng.pack(np.tile([[0, 0, 1.0]], (pair["dt"].shape[0], 1)))
