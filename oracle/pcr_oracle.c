@@ -27,7 +27,9 @@
  *   D2 neighbour order and ties: ascending (d2, index).
  *   D3 voxel output order: ascending linear voxel id (z, y, x lexicographic); sums in input order.
  *   D4 elementary functions: include/pcr_detmath.h.
- *   D5 order-free sums (inlier sum d2, ICP JtJ/Jtr) are int64 fixed point with power-of-two scales.
+ *   D5 order-free sums are int64: the inlier sum of d2 is fixed point with a power-of-two scale; the ICP normal
+ *      equations quantise J (6 entries) and r once per correspondence to kq-bit integers and sum exact integer
+ *      products (kq = min(30, (62 - ceil(log2 n)) / 2)).
  *   D6 RANSAC sampling: Philox4x32-10 keyed by seed, counter = global hypothesis index; result is
  *      that of the sequential (single-thread) Open3D loop.
  *   D7 ICP transforms the ORIGINAL fp32 source by the cumulative fp64 transform each pass.
