@@ -150,7 +150,10 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
 #define PCR_ICP_THREADS 256
 #endif
 constexpr int ICP_THREADS = PCR_ICP_THREADS;  // a multiple of 128 (the accumulate phase works on groups of 4 warps x 128 rows)
-constexpr int ICP_CTAS_PER_SM = 768 / ICP_THREADS;
+#ifndef PCR_ICP_CTAS
+#define PCR_ICP_CTAS (768 / PCR_ICP_THREADS)
+#endif
+constexpr int ICP_CTAS_PER_SM = PCR_ICP_CTAS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 
 // Result of the correspondence step for one source point: target index (-1: none), fp32 squared distance, and the
