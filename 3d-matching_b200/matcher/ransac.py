@@ -6,6 +6,9 @@ order and soft-failure behaviour; every Open3D / NumPy hot loop runs in libpcr_b
     compute_step_transformation      ransac.py:104-192  -> pcr_ransac_step
     evaluate_inlier_ratio            ransac.py:195-236  -> pcr_inlier_count
     evaluate_inlier_ratio_fast       ransac.py:239-277  -> pcr_inlier_count (squared)
+    run_ransac_manual                src/visualize_matcher/_visualize_matcher.py:343-470 (the GUI's step-by-step loop:
+                                     best = strictly greater inlier ratio, early stop, update callbacks) -> batched
+                                     pcr_ransac_step + pcr_inlier_count, the loop itself replayed on the host
 
 Keyword-only extras (never disturb positional use): confidence, seed.  Randomness is Philox keyed by
 (seed, hypothesis index) instead of the reference's unseeded global generators.
@@ -122,3 +125,72 @@ def evaluate_inlier_ratio_fast(p_src, p_tgt, transform, dist_thresh_sq: float) -
     T = torch.as_tensor(np.asarray(transform, np.float64).reshape(1, 4, 4))
     cnt = eng.inlier_count(device_cloud(p_src, eng), device_cloud(p_tgt, eng), corr, T, dist_thresh_sq, squared=True)
     return float(cnt[0].item()) / n
+
+
+def required_iterations(inlier_ratio: float, confidence: float = 0.99, sample_size: int = 3, max_iter: int = 0) -> int:
+    """RANSAC iteration count for a given inlier ratio (the GUI's compute_required_iterations,
+    _visualize_matcher.py:356-370): N = int(log(1 - confidence) / log(1 - ratio^sample_size)); ratio < 0.01 -> max_iter."""
+    if inlier_ratio < 0.01:
+        return int(max_iter)
+    with np.errstate(divide="ignore"):
+        return int(np.log(1 - confidence) / np.log(1 - inlier_ratio ** sample_size))
+
+
+def run_ransac_manual(src, tgt, voxel_size: float | None = None, max_iter: int = 1000, *, correspondences=None,
+                      noise_ratio: float = 2.0, early_stop_enabled: bool = True, early_stop_threshold: float = 0.5,
+                      early_stop_confidence: float = 0.99, update_interval: int = 10, callback=None, should_stop=None,
+                      seed: int = 0, batch: int = 4096) -> RegistrationResult:
+    """The step-by-step RANSAC of the reference's GUI worker (_visualize_matcher.py:343-470) with the same loop
+    semantics, minus the window: per iteration one 3-point Kabsch hypothesis (compute_step_transformation) scored by
+    evaluate_inlier_ratio_fast on the cached correspondence pairs with the squared threshold (1.5 v)^2; the best is
+    replaced only by a STRICTLY greater ratio (the first best wins ties, :426-429); early stop when
+    best > early_stop_threshold and iter >= required_iterations(best, confidence) (:432-450); `callback(result, iter,
+    ratio, best_ratio)` fires every `update_interval` iterations and on every new best (:453-466); `should_stop()` is
+    polled before each iteration (:396-409).  Defaults are MatcherSettings' (:151-173).
+
+    Hypotheses are generated and scored on the GPU `batch` at a time (two launches per batch) and the sequential loop
+    is replayed over them on the host, so the result is what the one-at-a-time loop returns for the same hypothesis
+    stream (Philox, seed) — iterations past an early stop are simply discarded.  Returns the best RegistrationResult
+    (fitness = inlier ratio; `.info` holds iterations, stopped_early, n_correspondences), or an identity result when
+    there are fewer than three correspondences (ransac.py:133-140)."""
+    voxel_size = voxel_of(src, voxel_size)
+    corres = compute_feature_correspondences(src, tgt, noise_ratio=noise_ratio, seed=seed) if correspondences is None \
+        else np.ascontiguousarray(np.asarray(correspondences), dtype=np.int32)
+    best = RegistrationResult()
+    best.info = {"iterations": 0, "stopped_early": False, "n_correspondences": int(len(corres))}
+    if len(corres) < 3 or max_iter <= 0:
+        return best
+    eng = get_engine()
+    s, t, c = device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corres, eng)
+    thresh_sq = (voxel_size * 1.5) ** 2
+    best_fitness, have_best, it = -1.0, False, 0
+    while it < max_iter:
+        n = min(batch, max_iter - it)
+        Ts = eng.ransac_step(s, t, c, seed, it, n)
+        w = (eng.inlier_count(s, t, c, Ts, thresh_sq, squared=True).cpu().numpy() / float(len(corres)))
+        Ts_h = None
+        for k in range(n):
+            if should_stop is not None and should_stop():
+                best.info.update(iterations=it, stopped_early=True)
+                return best
+            it += 1
+            w_cur = float(w[k])
+            is_new_best = (not have_best) or w_cur > best_fitness
+            if is_new_best or (callback is not None and it % update_interval == 0):
+                if Ts_h is None:
+                    Ts_h = Ts.cpu().numpy()
+                cur = RegistrationResult(Ts_h[k].copy(), w_cur, 0.0, None)
+                if is_new_best:
+                    info = best.info
+                    best, best_fitness, have_best = cur, w_cur, True
+                    best.info = info
+            if early_stop_enabled and best_fitness > early_stop_threshold and \
+                    it >= required_iterations(best_fitness, early_stop_confidence, 3, max_iter):
+                if callback is not None:
+                    callback(best, it, best_fitness, best_fitness)
+                best.info.update(iterations=it, stopped_early=True)
+                return best
+            if callback is not None and (it % update_interval == 0 or is_new_best):
+                callback(cur, it, w_cur, best_fitness)
+    best.info.update(iterations=it, stopped_early=False)
+    return best

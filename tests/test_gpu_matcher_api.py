@@ -199,3 +199,57 @@ def test_align_batch_workers_match_sequential(eng):
     assert np.array_equal(seq[2, :16], np.array(one.icp.transformation)) and seq[2, 16] == one.icp.fitness
     for i, (_, _, T) in enumerate(clouds):
         assert np.abs(seq[i, :16].reshape(4, 4)[:3, :3] - T[:3, :3]).max() < 5e-3 and seq[i, 16] > 0.9
+
+
+def test_run_ransac_manual_matches_the_gui_loop(eng):
+    """run_ransac_manual = the reference GUI worker's loop (_visualize_matcher.py:343-470): strictly-greater best,
+    early-stop formula, update callbacks — checked against a plain NumPy replay over the same hypothesis stream."""
+    from matcher.ransac import (compute_feature_correspondences, compute_step_transformations, required_iterations,
+                                run_ransac_manual)
+    from ply import Ply
+    v = 0.005
+    s, t, _ = synth.make_pair(12000, v, 909)
+    src, tgt = Ply.from_points(s, v), Ply.from_points(t, v)
+    corres = compute_feature_correspondences(src, tgt, noise_ratio=2.0, seed=4)
+    assert len(corres) == 3 * (len(corres) // 3) or len(corres) > 0
+    ps, pt = src.pcd_down.points[corres[:, 0]], tgt.pcd_down.points[corres[:, 1]]
+    thr2 = (1.5 * v) ** 2
+
+    def replay(max_iter, early, interval):
+        Ts = compute_step_transformations(src, tgt, corres, max_iter, seed=4, start=0).cpu().numpy()
+        best, bw, it, events = None, -1.0, 0, []
+        while it < max_iter:
+            T = Ts[it]
+            it += 1
+            d2 = (((ps @ T[:3, :3].T + T[:3, 3]) - pt) ** 2).sum(1)
+            w = float((d2 < thr2).sum()) / len(corres)
+            new = best is None or w > bw
+            if new:
+                best, bw = T, w
+            if early and bw > 0.5 and it >= required_iterations(bw, 0.99, 3, max_iter):
+                events.append(("stop", it))
+                return best, bw, it, True, events
+            if it % interval == 0 or new:
+                events.append(("upd", it))
+        return best, bw, it, False, events
+
+    for max_iter, early, interval in ((300, True, 10), (300, False, 7), (5000, True, 10)):
+        seen = []
+        r = run_ransac_manual(src, tgt, v, max_iter, correspondences=corres, early_stop_enabled=early, update_interval=interval,
+                              callback=lambda res, it, w, bw: seen.append(it), seed=4, batch=128)
+        T, bw, it, stopped, events = replay(max_iter, early, interval)
+        # the device counts inliers with the same strict squared threshold; ratios are integer counts / C, so equal
+        assert r.info["iterations"] == it and r.info["stopped_early"] == stopped
+        assert abs(r.fitness - bw) < 1e-12 and np.allclose(r.transformation, T, atol=1e-12)
+        assert seen == [e[1] for e in events]
+    # cooperative stop: polled before every iteration
+    calls = {"n": 0}
+
+    def stop():
+        calls["n"] += 1
+        return calls["n"] > 25
+    r = run_ransac_manual(src, tgt, v, 1000, correspondences=corres, should_stop=stop, early_stop_enabled=False, seed=4)
+    assert r.info["iterations"] == 25 and r.info["stopped_early"]
+    # fewer than three correspondences: identity, fitness 0 (ransac.py:133-140)
+    r = run_ransac_manual(src, tgt, v, 100, correspondences=corres[:2])
+    assert np.array_equal(r.transformation, np.eye(4)) and r.fitness == 0.0
