@@ -392,11 +392,13 @@ def run_aux(eng, args, world, rank, peaks):
     from pcr_b200.dist import align_batch
     B = args.batch_pairs
     if B > 0:
-        pairs = []
+        pairs, host_pairs = [], {}
         for i in range(B * world):
             if i % world == rank:
                 s_i, t_i, _ = synth.make_pair(50000, v, 30000 + i)
                 pairs.append((eng.pack(s_i), eng.pack(t_i)))
+                if len(host_pairs) < 2:
+                    host_pairs[i] = (s_i, t_i)
             else:
                 pairs.append(None)
         pb = eng.default_params(v)
@@ -418,6 +420,18 @@ def run_aux(eng, args, world, rank, peaks):
                 dt = float(t.item())
             batch[f"pairs_per_s_workers{workers}"] = B * world / dt
             batch[f"min_fitness_workers{workers}"] = float(tab[:, 16].min())
+        if rank == 0 and not args.no_cpu:  # per-pair parity with the oracle on a sample (the checker, not the thing measured)
+            from oracle import pcr_oracle as orc
+            orc.build()
+            orc.set_num_threads(host_threads())
+            same = True
+            for i, (s_i, t_i) in host_pairs.items():
+                S_, G_ = orc.preprocess(s_i, v), orc.preprocess(t_i, v)
+                ro = orc.global_registration(S_, G_, v, RANSAC_ITERS, 0.999, 7)
+                io = orc.refine_registration(S_, G_, ro.transformation, v)
+                same = same and np.array_equal(tab[i, :16].reshape(4, 4), io.transformation) and tab[i, 16] == io.fitness
+            batch["oracle_checked_pairs"] = len(host_pairs)
+            batch["identical_to_oracle"] = bool(same)
         out["batch"] = batch
         del pairs
     # ICP at 1M points: replicas only (single-pair ICP does not shard); aggregate = world x per-GPU rate
