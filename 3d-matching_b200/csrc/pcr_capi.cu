@@ -228,15 +228,39 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     if (!(v > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "voxel_size must be > 0");
     if (ns <= 0 || nt <= 0) return pcr_fail(ctx, PCR_ERR_INVALID, "Point cloud is empty");  // src/ply/ply.py:81-84
     static const bool overlap = !(getenv("PCR_ALIGN_OVERLAP") && atoi(getenv("PCR_ALIGN_OVERLAP")) == 0);
+    static const bool use_prio = !(getenv("PCR_ALIGN_PRIORITY") && atoi(getenv("PCR_ALIGN_PRIORITY")) == 0);
+    pcr_ctx *h = nullptr;
+    if (overlap) PCR_TRY(pcr_helper_get(ctx, &h));
+    // While the helper context works, the critical path (this thread's kernels) runs on a highest-priority stream, so
+    // that its CTAs are dispatched ahead of the helper's queued ones; the call ends with a full synchronisation, so
+    // the caller's stream sees no difference.  The guard restores ctx->stream on every return path.
+    struct StreamSwap {
+        pcr_ctx *c;
+        cudaStream_t saved;
+        bool on;
+        ~StreamSwap() {
+            if (on) {
+                cudaStreamSynchronize(c->stream);
+                c->stream = saved;
+            }
+        }
+    } swap{ctx, ctx->stream, false};
+    if (overlap && use_prio && ctx->hp_stream) {
+        cudaEvent_t in_ready;
+        PCR_CUDA(cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(in_ready, ctx->stream));
+        PCR_CUDA(cudaStreamWaitEvent(ctx->hp_stream, in_ready, 0));
+        PCR_CUDA(cudaEventDestroy(in_ready));
+        ctx->stream = ctx->hp_stream;
+        swap.on = true;
+    }
     StageTimer tm(ctx->stream);
     tm.mark();
     float4 *sd = nullptr, *td = nullptr, *sn = nullptr, *tn = nullptr, *tfn = nullptr;
     float *sf = nullptr, *tf = nullptr;
     int ms = 0, mt = 0;
-    pcr_ctx *h = nullptr;
     cudaEvent_t ready = nullptr;
     if (overlap) {
-        PCR_TRY(pcr_helper_get(ctx, &h));
         // the clouds were produced on the main stream: the helper stream waits for them
         PCR_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         PCR_CUDA(cudaEventRecord(ready, ctx->stream));

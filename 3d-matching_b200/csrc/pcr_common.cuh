@@ -96,6 +96,7 @@ struct pcr_ctx {
     pcr_ctx *helper = nullptr;
     struct Worker *worker = nullptr;
     bool owns_stream = false;
+    cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
 };
 
 // one persistent host thread executing one task at a time

@@ -153,6 +153,12 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
             return pcr_fail(ctx, PCR_ERR_CUDA, "cannot create the helper stream");
         }
         h->owns_stream = true;
+        int prio_low = 0, prio_high = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+        if (cudaStreamCreateWithPriority(&ctx->hp_stream, cudaStreamNonBlocking, prio_high) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->hp_stream = nullptr;
+        }
         ctx->helper = h;
         ctx->worker = new Worker();
     }
@@ -207,6 +213,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
     delete ctx;
     return PCR_OK;
 }
