@@ -8,7 +8,8 @@ typedef unsigned long long u64;
 // implementation functions (one per translation unit)
 int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, const float4 *nrm, int nt,
                  double max_dist, const double *init, int max_iter, double rel_fit, double rel_rmse,
-                 pcr_reg_result *res, int *corr, bool sync_result);
+                 pcr_reg_result *res, int *corr, bool sync_result, const IcpPrep *prepared = nullptr);
+int pcr_icp_prepare(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, double max_dist, IcpPrep *prep);
 int pcr_nn1_impl(pcr_ctx *ctx, const float4 *tgt, int nt, const float4 *q, int nq, double radius, int *idx, float *d2);
 int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq, double radius, int max_nn, int *idx,
                  float *d2, int *cnt);
@@ -279,11 +280,15 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     tm.mark();
     tm.mark();
     // Ply._add_normals on the full-resolution clouds (src/ply/ply.py:65,133-135): next to matching + RANSAC
-    auto full_normals = [=, &tfn](pcr_ctx *c) -> int {
+    IcpPrep icp_prep;
+    pcr_ctx *const main_ctx = ctx;
+    auto full_normals = [=, &tfn, &icp_prep](pcr_ctx *c) -> int {
         pcr_ctx *ctx = c;
         PCR_ALLOC(t, float4, (size_t)nt);
         PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, t));
         tfn = t;
+        // the ICP search structures depend only on the clouds: built here, off the critical path
+        if (c != main_ctx) PCR_TRY(pcr_icp_prepare(ctx, src, ns, tgt, nt, 0.4 * v, &icp_prep));
         if (p->source_normals) {
             PCR_ALLOC(sfn, float4, (size_t)ns);
             PCR_TRY(pcr_normals_impl(ctx, src, ns, 2.0 * v, 30, sfn));
@@ -317,7 +322,7 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     tm.mark();
     // refine_registration (src/matcher/icp.py:41-48): full-resolution clouds, threshold 0.4 v
     PCR_TRY(pcr_icp_impl(ctx, src, ns, tgt, tfn, nt, 0.4 * v, res->ransac.transformation, p->icp_max_iter,
-                         p->icp_rel_fitness, p->icp_rel_rmse, &res->icp, nullptr, true));
+                         p->icp_rel_fitness, p->icp_rel_rmse, &res->icp, nullptr, true, &icp_prep));
     tm.mark();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     res->n_src_down = ms;

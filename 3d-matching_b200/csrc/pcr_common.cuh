@@ -49,6 +49,14 @@ struct Grid {
 };
 
 
+// prepared ICP work: everything that depends only on the two clouds (pcr_icp.cu); may be built on another context
+struct IcpPrep {
+    Grid g;
+    const float4 *src_sorted = nullptr;
+    float amax = 0.0f;
+    bool valid = false;
+};
+
 // prepared RANSAC work (target grid + spatially sorted source), see pcr_ransac.cu
 struct RansacWork {
     Grid g;

@@ -520,9 +520,23 @@ int pcr_sort_cloud_spatially(pcr_ctx *ctx, const float4 *pts, int n, double cell
     return PCR_OK;
 }
 
+// target grid for radius max_dist, Morton-sorted source, largest |target coordinate| (for the fixed-point scale)
+int pcr_icp_prepare(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, double max_dist, IcpPrep *prep) {
+    prep->valid = false;
+    if (!(max_dist > 0.0) || ns <= 0 || nt <= 0) return PCR_OK;  // pcr_icp_impl reports / handles these cases
+    float lo[3], hi[3];
+    PCR_TRY(pcr_bounds(ctx, tgt, nt, lo, hi));
+    prep->amax = 0.0f;
+    for (int d = 0; d < 3; d++) prep->amax = fmaxf(prep->amax, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
+    PCR_TRY(pcr_grid_build(ctx, tgt, nt, max_dist, lo, hi, &prep->g));
+    PCR_TRY(pcr_morton_sort(ctx, src, ns, &prep->src_sorted));
+    prep->valid = true;
+    return PCR_OK;
+}
+
 int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, const float4 *nrm, int nt,
                  double max_dist, const double *init, int max_iter, double rel_fit, double rel_rmse,
-                 pcr_reg_result *res, int *corr, bool sync_result) {
+                 pcr_reg_result *res, int *corr, bool sync_result, const IcpPrep *prepared) {
     memset(res, 0, sizeof(*res));
     for (int i = 0; i < 16; i++) res->transformation[i] = init[i];
     res->best_hyp = -1;
@@ -532,15 +546,14 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
         if (corr && ns > 0) PCR_CUDA(cudaMemsetAsync(corr, 0xff, sizeof(int) * (size_t)ns, ctx->stream));
         return PCR_OK;
     }
-    // target grid (bounds needed anyway for the fixed-point scale)
-    float lo[3], hi[3];
-    PCR_TRY(pcr_bounds(ctx, tgt, nt, lo, hi));
-    float amax = 0.0f;
-    for (int d = 0; d < 3; d++) amax = fmaxf(amax, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
-    Grid g;
-    PCR_TRY(pcr_grid_build(ctx, tgt, nt, max_dist, lo, hi, &g));
-    const float4 *src_sorted = nullptr;
-    PCR_TRY(pcr_morton_sort(ctx, src, ns, &src_sorted));
+    IcpPrep own;
+    if (!(prepared && prepared->valid)) {
+        PCR_TRY(pcr_icp_prepare(ctx, src, ns, tgt, nt, max_dist, &own));
+        prepared = &own;
+    }
+    const float amax = prepared->amax;
+    Grid g = prepared->g;
+    const float4 *src_sorted = prepared->src_sorted;
 
     const int lg = pcr_ilog2ceil(ns > 1 ? ns : 1);
     const int e_r = pcr_pow2ceil_exp(max_dist);
