@@ -253,3 +253,32 @@ def test_run_ransac_manual_matches_the_gui_loop(eng):
     # fewer than three correspondences: identity, fitness 0 (ransac.py:133-140)
     r = run_ransac_manual(src, tgt, v, 100, correspondences=corres[:2])
     assert np.array_equal(r.transformation, np.eye(4)) and r.fitness == 0.0
+
+
+def test_align_deterministic_under_overlap_and_threads(eng):
+    """pcr_align overlaps stages on a helper context and may be called from several host threads (one context each):
+    every run must return the same bits (tools/gpu_stress_align.py is the long version)."""
+    import threading
+    import torch
+    from pcr_b200.engine import Engine
+    v = 0.005
+    src, tgt, _ = synth.make_pair(15000, v, 4711)
+
+    def run(e, out, reps):
+        ds, dt = e.pack(src), e.pack(tgt)
+        p = e.default_params(v)
+        p.ransac_max_iter = 20000
+        p.seed = 5
+        for _ in range(reps):
+            r = e.align_device(ds, dt, p)
+            out.append((tuple(r.icp.transformation), r.icp.fitness, r.icp.inlier_rmse, r.ransac.best_hyp, r.icp.iterations))
+    base = []
+    run(eng, base, 10)
+    assert all(x == base[0] for x in base)
+    outs = [[], []]
+    ths = [threading.Thread(target=lambda k=k: (torch.cuda.set_device(eng.tdev), run(Engine(eng.tdev.index), outs[k], 10))) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert all(len(o) == 10 and all(x == base[0] for x in o) for o in outs)
