@@ -206,6 +206,18 @@ static int preprocess_cloud(pcr_ctx *c, const float4 *pts, int n, double v, floa
     pcr_ctx *ctx = c;
     PCR_ALLOC(d, float4, (size_t)n);
     PCR_TRY(pcr_voxel_impl(ctx, pts, n, v, d, m));
+    {
+        // the voxel centroids lie inside the bounding box of the cloud they average: that box (cached by the voxel
+        // stage) serves as the box of the search grids over the down-sampled cloud — grids are only search structures,
+        // no result depends on their origin — and saves a reduction + host synchronisation per cloud
+        float lo[3], hi[3];
+        PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));  // cache hit
+        pcr_ctx::BoundsEntry e;
+        e.ptr = d;
+        e.n = *m;
+        for (int k = 0; k < 3; k++) { e.lo[k] = lo[k]; e.hi[k] = hi[k]; }
+        ctx->bounds_cache.push_back(e);
+    }
     PCR_ALLOC(nn, float4, (size_t)*m);
     PCR_TRY(pcr_normals_impl(ctx, d, *m, 2.0 * v, 30, nn));
     PCR_ALLOC(f, float, (size_t)*m * 33);
