@@ -662,7 +662,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
     std::vector<pcr_hyp_record> recs;
     static const int wave_first = getenv("PCR_WAVE_FIRST") ? atoi(getenv("PCR_WAVE_FIRST")) : 2048;
-    static const int wave_growth = getenv("PCR_WAVE_GROWTH") ? atoi(getenv("PCR_WAVE_GROWTH")) : 8;
+    static const int wave_growth = getenv("PCR_WAVE_GROWTH") ? atoi(getenv("PCR_WAVE_GROWTH")) : 64;
     int64_t begin = 0, wave = wave_first;  // small blind first wave (no best to prune against yet), then growing to fill the GPU
     int64_t survivors = 0;
     while (begin < max_iter && begin < res->est_k) {
@@ -683,7 +683,9 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
         pcr_ransac_scan(recs.data(), nrec, begin, end, c, ms, confidence, w.k_d, res, &stop);
         begin = end;
         if (stop) break;
-        if (wave < (1 << 20)) wave *= wave_growth;
+        // completed evaluations are shared inside a wave (bucket_best), so the second wave can be large: measured
+        // (2048, x8) 1.22 ms, (2048, x64) 1.09 ms, (4096, x64) 1.12 ms, (1024, x128) 1.07 ms for 100k hypotheses
+        wave = std::min<int64_t>(wave * wave_growth, 1 << 20);
     }
     res->survivors = survivors;
     res->k_d = w.k_d;
