@@ -52,15 +52,15 @@ def _wave_fn_factory(orc, sd, td, corr, max_dist, seed):
     return wave_fn
 
 
-def _worker(rank, world, port, conf, max_iter, q):
+def _worker(rank, world, port, conf, max_iter, q, fixed_cap=None):
     try:
-        _worker_body(rank, world, port, conf, max_iter, q)
+        _worker_body(rank, world, port, conf, max_iter, q, fixed_cap)
     except Exception as e:  # surface the failure instead of letting the parent wait for its timeout
         q.put(("error", repr(e)))
         raise
 
 
-def _worker_body(rank, world, port, conf, max_iter, q):
+def _worker_body(rank, world, port, conf, max_iter, q, fixed_cap=None):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -68,7 +68,10 @@ def _worker_body(rank, world, port, conf, max_iter, q):
     orc, v, sd, td, corr = _problem()
     orc.set_num_threads(1)
     from pcr_b200 import _capi
+    from pcr_b200 import dist as pdist
     from pcr_b200.dist import ransac_distributed
+    if fixed_cap is not None:
+        pdist.FIXED_CAP = fixed_cap  # force the second all-gather (a chain longer than the per-wave record budget)
     lib = _capi.load()
     import ctypes as C
     k_d = int(lib.pcr_ransac_k_d(C.c_double(1.5 * v), C.c_int(len(sd))))
@@ -80,14 +83,14 @@ def _worker_body(rank, world, port, conf, max_iter, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("conf,max_iter", [(0.999, 3000), (1.0, 600)])
-def test_two_ranks_reproduce_the_sequential_result(conf, max_iter):
+@pytest.mark.parametrize("conf,max_iter,fixed_cap", [(0.999, 3000, None), (1.0, 600, None), (1.0, 400, 1)])
+def test_two_ranks_reproduce_the_sequential_result(conf, max_iter, fixed_cap):
     orc, v, sd, td, corr = _problem()
     want = orc.ransac(sd, td, corr, 1.5 * v, max_iter, conf, seed=3)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, conf, max_iter, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, conf, max_iter, q, fixed_cap)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=240) for _ in procs]
