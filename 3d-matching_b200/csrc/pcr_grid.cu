@@ -75,73 +75,29 @@ int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3])
     return PCR_OK;
 }
 
-// ---- exclusive scan (3 phases: tile sums, scan of tile sums, tile scan + offset) -------------------------
-template <typename T>
-__global__ void __launch_bounds__(1024) k_scan_tile_sums(const T *__restrict__ data, long long n, T *__restrict__ sums) {
-    constexpr int ITEMS = 4;
-    const long long base = (long long)blockIdx.x * (1024 * ITEMS);
-    T s = 0;
-#pragma unroll
-    for (int k = 0; k < ITEMS; k++) {
-        const long long i = base + (long long)k * 1024 + threadIdx.x;
-        if (i < n) s += data[i];
-    }
-    __shared__ T ws[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        T v = ws[threadIdx.x];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) sums[blockIdx.x] = v;
-    }
-}
-
-// single block: exclusive scan of m tile sums in place; total -> sums[m]
-template <typename T>
-__global__ void __launch_bounds__(1024) k_scan_sums(T *__restrict__ sums, int m) {
-    __shared__ T ws[32];
-    __shared__ T carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < m; base += 1024) {
-        const int i = base + threadIdx.x;
-        const T v = i < m ? sums[i] : (T)0;
-        T x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const T y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            T w = ws[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const T y = __shfl_up_sync(0xffffffffu, w, o);
-                if (threadIdx.x >= o) w += y;
-            }
-            ws[threadIdx.x] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const T warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : (T)0;
-        const T incl = x + warp_off + carry;
-        if (i < m) sums[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) sums[m] = carry;
+// ---- single-pass exclusive scan (decoupled look-back) ----------------------------------------------------------------
+// One kernel instead of three (tile sums / scan of sums / tiles): a tile takes a ticket (so every earlier tile is
+// already running), publishes its aggregate, and warp 0 walks back over the 32 nearest predecessors at a time until
+// it meets an inclusive prefix.  state[t] = (flag << 62) | value, flag 1 = aggregate, 2 = inclusive prefix; values stay
+// below 2^62 (they are point counts).  state and the ticket are zeroed before the launch.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024) k_scan_tiles(T *__restrict__ data, long long n, const T *__restrict__ sums) {
+__global__ void __launch_bounds__(1024) k_scan_onepass(T *__restrict__ data, long long n, unsigned long long *__restrict__ state,
+                                                       unsigned int *__restrict__ ticket) {
     constexpr int ITEMS = 4;
-    // thread t owns ITEMS consecutive elements so the tile is scanned in memory order
-    const long long base = (long long)blockIdx.x * (1024 * ITEMS) + (long long)threadIdx.x * ITEMS;
+    typedef unsigned long long u64s;
+    __shared__ T ws[32];
+    __shared__ unsigned int s_tile;
+    __shared__ T s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const long long tile = s_tile;
+    const long long base = tile * (1024 * ITEMS) + (long long)threadIdx.x * ITEMS;
     T v[ITEMS];
     T s = 0;
 #pragma unroll
@@ -149,7 +105,6 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(T *__restrict__ data, long 
         v[k] = (base + k < n) ? data[base + k] : (T)0;
         s += v[k];
     }
-    __shared__ T ws[32];
     T x = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -165,29 +120,67 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(T *__restrict__ data, long 
             const T y = __shfl_up_sync(0xffffffffu, w, o);
             if (threadIdx.x >= o) w += y;
         }
-        ws[threadIdx.x] = w;
+        ws[threadIdx.x] = w;  // inclusive over warps; ws[31] = tile aggregate
+        const T aggregate = __shfl_sync(0xffffffffu, w, 31);
+        const int lane = threadIdx.x;
+        T prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state + tile, (2ull << 62) | (u64s)aggregate);
+            }
+        } else {
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state + tile, (1ull << 62) | (u64s)aggregate);
+            }
+            long long j = tile - 1;
+            for (;;) {
+                const long long idx = j - lane;
+                u64s w2;
+                for (;;) {  // wait until the 32 predecessors of this window have published something
+                    w2 = idx >= 0 ? ld_acquire_u64(state + idx) : (2ull << 62);  // before tile 0: inclusive prefix 0
+                    if (__ballot_sync(0xffffffffu, (w2 >> 62) == 0ull) == 0u) break;
+                }
+                const unsigned int incl = __ballot_sync(0xffffffffu, (w2 >> 62) == 2ull);
+                const int first = incl ? (__ffs(incl) - 1) : 32;  // nearest predecessor with an inclusive prefix
+                T part = (lane <= first) ? (T)(w2 & ((1ull << 62) - 1ull)) : (T)0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (incl) break;
+                j -= 32;
+            }
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(state + tile, (2ull << 62) | (u64s)(prefix + aggregate));
+            }
+        }
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    T run = (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : (T)0) + sums[blockIdx.x];
+    T run = (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : (T)0) + s_prefix;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         if (base + k < n) data[base + k] = run;
         run += v[k];
     }
+    // data[n] receives the total: the thread that owns element n - 1 has it
+    if (base <= n - 1 && n - 1 < base + ITEMS) data[n] = run;
 }
 
 template <typename T>
 static int exclusive_scan_impl(pcr_ctx *ctx, T *data, long long n) {
     // data has n+1 slots; data[n] receives the total
+    if (n <= 0) {
+        if (n == 0) PCR_CUDA(cudaMemsetAsync(data, 0, sizeof(T), ctx->stream));
+        return PCR_OK;
+    }
     const int tiles = div_up(n, 4096);
-    PCR_ALLOC(sums, T, (size_t)tiles + 1);
-    k_scan_tile_sums<T><<<tiles, 1024, 0, ctx->stream>>>(data, n, sums);
+    PCR_ALLOC(state, unsigned long long, (size_t)tiles + 1);  // [tiles] flags + values, then the ticket
+    PCR_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * ((size_t)tiles + 1), ctx->stream));
+    k_scan_onepass<T><<<tiles, 1024, 0, ctx->stream>>>(data, n, state, (unsigned int *)(state + tiles));
     PCR_LAUNCHED();
-    k_scan_sums<T><<<1, 1024, 0, ctx->stream>>>(sums, tiles);
-    PCR_LAUNCHED();
-    k_scan_tiles<T><<<tiles, 1024, 0, ctx->stream>>>(data, n, sums);
-    PCR_LAUNCHED();
-    PCR_CUDA(cudaMemcpyAsync(data + n, sums + tiles, sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     PCR_CUDA(cudaGetLastError());
     return PCR_OK;
 }
