@@ -608,12 +608,12 @@ ORC_API int orc_fpfh(const float *pts, const float *normals, int n, double radiu
                 const double dist = (double)nb_d2[(size_t)i * K + k];
                 if (dist == 0.0) continue;
                 const double *hs = spfh + (size_t)nb_idx[(size_t)i * K + k] * 33;
-                for (int j = 0; j < 33; j++) {
-                    const double val = hs[j] / dist;
-                    sum[j / 11] += val;
-                    F[j] += val;
-                }
+                for (int j = 0; j < 33; j++) F[j] += hs[j] / dist;
             }
+            /* D8: the normaliser of a block is the sum of its 11 accumulated bins, in bin order (Open3D keeps a running
+             * sum over (neighbour, bin) instead: the same real number, rounded along another path) */
+            for (int b = 0; b < 3; b++)
+                for (int j = 0; j < 11; j++) sum[b] += F[11 * b + j];
             for (int b = 0; b < 3; b++) if (sum[b] != 0.0) sum[b] = 100.0 / sum[b];
             const double *hi = spfh + (size_t)i * 33;
             for (int j = 0; j < 33; j++) F[j] = F[j] * sum[j / 11] + hi[j];
