@@ -70,6 +70,7 @@ struct pcr_ctx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<KPending> pending;
     double k_ms[KC_COUNT] = {0};
+    double k_ms_helper[KC_COUNT] = {0};  // share of k_ms measured on the helper context
     double k_bytes[KC_COUNT] = {0};
     double k_flops[KC_COUNT] = {0};
     long long k_launches[KC_COUNT] = {0};

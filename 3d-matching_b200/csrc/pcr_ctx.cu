@@ -269,6 +269,7 @@ int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset) {
             float ms = 0.0f;
             if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
                 ctx->k_ms[p.id] += ms;
+                ctx->k_ms_helper[p.id] += ms;
                 ctx->k_launches[p.id] += p.launches;
                 ctx->k_bytes[p.id] += p.bytes * (double)p.launches;
                 ctx->k_flops[p.id] += p.flops * (double)p.launches;
@@ -282,10 +283,12 @@ int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset) {
     }
     for (int i = 0; i < KC_COUNT; i++) {
         out[i].total_ms = ctx->k_ms[i];
+        out[i].overlapped_ms = ctx->k_ms_helper[i];
         out[i].launches = ctx->k_launches[i];
         out[i].bytes = ctx->k_bytes[i];
         out[i].flops = ctx->k_flops[i];
         if (reset) {
+            ctx->k_ms_helper[i] = 0;
             ctx->k_ms[i] = 0;
             ctx->k_launches[i] = 0;
             ctx->k_bytes[i] = 0;

@@ -52,7 +52,8 @@ class HypRecord(C.Structure):
 
 class KernelStat(C.Structure):
     """pcr_kernel_stat"""
-    _fields_ = [("total_ms", C.c_double), ("launches", C.c_int64), ("bytes", C.c_double), ("flops", C.c_double)]
+    _fields_ = [("total_ms", C.c_double), ("launches", C.c_int64), ("bytes", C.c_double), ("flops", C.c_double),
+                ("overlapped_ms", C.c_double)]
 
 
 class AlignParams(C.Structure):

@@ -91,7 +91,7 @@ class Engine:
         with self._lock:
             self._bind_stream()
             self._check(self.lib.pcr_kernel_stats(self.ctx, arr, C.c_int(n), C.c_int(int(reset))))
-        return {self.lib.pcr_kernel_class_name(i).decode(): {"ms": arr[i].total_ms, "launches": arr[i].launches,
+        return {self.lib.pcr_kernel_class_name(i).decode(): {"ms": arr[i].total_ms, "overlapped_ms": arr[i].overlapped_ms, "launches": arr[i].launches,
                                                               "bytes": arr[i].bytes, "flops": arr[i].flops}
                 for i in range(n) if arr[i].launches}
 

@@ -259,7 +259,12 @@ def run_engine(args):
     ms_default, res_d = timed(lambda: eng.align_host(src_pin, tgt_pin, p_default), args.steps, 1)
 
     # ---- roofline of the dominant kernel class -----------------------------------------------------------------------
-    dom = max(kstats.items(), key=lambda kv: kv[1]["ms"]) if kstats else None
+    # dominant kernel class of the CRITICAL PATH: time a class spends on pcr_align's helper context (full-resolution
+    # normals, ICP search structures) overlaps the critical path and is time-sliced with it, so it is reported
+    # separately (aux.kernel_ms_overlapped_per_step) and does not take part in the selection
+    def crit(st):
+        return st["ms"] - st.get("overlapped_ms", 0.0)
+    dom = max(kstats.items(), key=lambda kv: crit(kv[1])) if kstats else None
     roof = None
     step_total = sum(v["ms"] for v in kstats.values()) or 1.0
     if dom:
@@ -311,6 +316,7 @@ def run_engine(args):
                ["preprocess_both_clouds", "_unused1", "_unused2", "match", "ransac",
                 "wait_for_full_res_normals_overlapped_with_ransac", "icp", "total"], res.stage_ms) if not k.startswith("_")},
            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
+           "kernel_ms_overlapped_per_step": {k: v["overlapped_ms"] / args.steps for k, v in kstats.items() if v.get("overlapped_ms", 0.0) > 0.0},
            "icp_pass_roofline_100k": icp_roof}
     if not args.no_aux:
         aux.update(run_aux(eng, args, world, rank, peaks))

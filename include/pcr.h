@@ -90,6 +90,8 @@ typedef struct pcr_kernel_stat {
     int64_t launches;
     double bytes;
     double flops;
+    double overlapped_ms; /* part of total_ms spent on pcr_align's helper context, i.e. off the critical path and
+                           * time-sliced with the critical path's kernels */
 } pcr_kernel_stat;
 PCR_API int pcr_set_profiling(pcr_ctx *ctx, int enabled);
 PCR_API int pcr_kernel_class_count(void);
