@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         L.count = L.sumq = 0;
         L.pass = L.done = L.iterations = L.converged = 0;
     }
-    const double scJ = S->sc_J, scR = S->sc_R, scd = S->sc_d;
+    const double scd = S->sc_d;
+    const float scJf = (float)S->sc_J, scRf = (float)S->sc_R;  // powers of two: exact in fp32
     const double isc_JJ = S->isc_JJ, isc_Jr = S->isc_Jr, isc_d = S->isc_d, rel_fit = S->rel_fit, rel_rmse = S->rel_rmse;
     const int max_iter = S->max_iter, trace = S->trace;
     const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
@@ -352,15 +353,19 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
                 IcpMatch m;
                 icp_point_nn(g, tgt, nrm, q, r2, max_dist_f, pass, i, st0, st1, st2, cert2, m);
                 if (m.j >= 0) {
-                    const double sx = q.x, sy = q.y, sz = q.z;
-                    const double nx = m.nx, ny = m.ny, nz = m.nz;
-                    q0 = __double2int_rn(__dmul_rn(sy * nz - sz * ny, scJ));
-                    q1 = __double2int_rn(__dmul_rn(sz * nx - sx * nz, scJ));
-                    q2 = __double2int_rn(__dmul_rn(sx * ny - sy * nx, scJ));
-                    q3 = __double2int_rn(__dmul_rn(nx, scJ));
-                    q4 = __double2int_rn(__dmul_rn(ny, scJ));
-                    q5 = __double2int_rn(__dmul_rn(nz, scJ));
-                    q6 = __double2int_rn(__dmul_rn(((sx - (double)m.tx) * nx + (sy - (double)m.ty) * ny) + (sz - (double)m.tz) * nz, scR));
+                    // point-to-plane row in fp32, every operation individually rounded (as the oracle): J and r are
+                    // quantised to kq <= 30 bits right here, so fp64 bought nothing but fp64-pipe time
+                    const float sx = q.x, sy = q.y, sz = q.z;
+                    const float nx = m.nx, ny = m.ny, nz = m.nz;
+                    const float ex = __fsub_rn(sx, m.tx), ey = __fsub_rn(sy, m.ty), ez = __fsub_rn(sz, m.tz);
+                    const float r = __fadd_rn(__fadd_rn(__fmul_rn(ex, nx), __fmul_rn(ey, ny)), __fmul_rn(ez, nz));
+                    q0 = __float2int_rn(__fmul_rn(__fsub_rn(__fmul_rn(sy, nz), __fmul_rn(sz, ny)), scJf));
+                    q1 = __float2int_rn(__fmul_rn(__fsub_rn(__fmul_rn(sz, nx), __fmul_rn(sx, nz)), scJf));
+                    q2 = __float2int_rn(__fmul_rn(__fsub_rn(__fmul_rn(sx, ny), __fmul_rn(sy, nx)), scJf));
+                    q3 = __float2int_rn(__fmul_rn(nx, scJf));
+                    q4 = __float2int_rn(__fmul_rn(ny, scJf));
+                    q5 = __float2int_rn(__fmul_rn(nz, scJf));
+                    q6 = __float2int_rn(__fmul_rn(r, scRf));
                     cnt++;
                     sumq += fixed_ll((double)m.d2, scd);
                 }

@@ -1120,13 +1120,16 @@ ORC_API int orc_icp_point_to_plane(const float *src, int ns, const float *tgt, c
                 if (!kd_hybrid(tt, q, r2, 1, &b)) { corr[i] = -1; continue; }
                 corr[i] = b.idx;
                 const float *tp = tgt + 3 * b.idx, *np = tgt_normals + 3 * b.idx;
-                const double sx = q[0], sy = q[1], sz = q[2];
-                const double nx = np[0], ny = np[1], nz = np[2];
-                const double r = (((sx - (double)tp[0]) * nx + (sy - (double)tp[1]) * ny)) + (sz - (double)tp[2]) * nz;
-                const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+                /* point-to-plane row in fp32 (every operation individually rounded, no FMA): J and r are quantised to
+                 * kq <= 30 bits right after, so fp64 here bought nothing but fp64-pipe time on the device */
+                const float sx = q[0], sy = q[1], sz = q[2];
+                const float nx = np[0], ny = np[1], nz = np[2];
+                const float ex = sx - tp[0], ey = sy - tp[1], ez = sz - tp[2];
+                const float r = ((ex * nx) + (ey * ny)) + (ez * nz);
+                const float J[6] = {(sy * nz) - (sz * ny), (sz * nx) - (sx * nz), (sx * ny) - (sy * nx), nx, ny, nz};
                 long long qJ[6];
-                for (int a = 0; a < 6; a++) qJ[a] = llrint(ldexp(J[a], s_J));
-                const long long qr = llrint(ldexp(r, s_R));
+                for (int a = 0; a < 6; a++) qJ[a] = llrintf(ldexpf(J[a], s_J));
+                const long long qr = llrintf(ldexpf(r, s_R));
                 int e = 0;
                 for (int a = 0; a < 6; a++)
                     for (int c = a; c < 6; c++) A->JJ[e++] += qJ[a] * qJ[c];
