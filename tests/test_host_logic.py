@@ -136,3 +136,28 @@ def test_synth_is_deterministic_and_consistent():
     assert np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-12)
     moved = src.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
     assert abs(np.linalg.norm(moved.mean(0) - tgt.mean(0))) < 0.1 * np.ptp(tgt)
+
+
+def test_required_iterations_formula():
+    """The GUI worker's early-stop bound (src/visualize_matcher/_visualize_matcher.py:356-370):
+    int(log(1 - confidence) / log(1 - ratio^3)), max_iter below a 1 % inlier ratio."""
+    import math
+    from matcher.ransac import required_iterations
+    assert required_iterations(0.005, 0.99, 3, 1234) == 1234
+    for ratio, conf in ((0.5, 0.99), (0.9, 0.99), (0.51, 0.999), (0.2, 0.9)):
+        assert required_iterations(ratio, conf, 3, 10) == int(math.log(1 - conf) / math.log(1 - ratio ** 3))
+    assert required_iterations(0.5, 0.99) == 34
+    assert required_iterations(1.0, 0.99) == 0  # log(0) = -inf: the loop stops at once
+
+
+def test_benchmark_cli_arguments_match_the_reference():
+    """Same flags and defaults as the reference's benchmark_ransac.py:283-343 (the run itself needs a GPU)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "3d-matching_b200", "benchmark_ransac.py")).read()
+    for flag, default in (("--source", '"sample.ply"'), ("--target", '"target.ply"'), ("--voxel-size", "0.3"),
+                          ("--noise-ratio", "0.0"), ("--test-iterations", "100"), ("--ransac-iterations", "30")):
+        line = next(ln for ln in src.splitlines() if f'"{flag}"' in ln)
+        assert f"default={default}" in line, line
+    assert importlib.util.find_spec("torch") is not None
