@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o barrier_bench barrier_bench.cu   (run on a B200: ./barrier_bench)
 // Micro-benchmark: grid-barrier variants for the persistent ICP kernel (cycles per barrier incl. 29 data atomics).
 #include <cstdio>
 #include <cuda_runtime.h>
