@@ -17,6 +17,7 @@ PCR_ERR_CUDA = -2
 PCR_ERR_OOM = -3
 PCR_ERR_BUSY = -4
 PCR_ERR_TOO_LARGE = -5
+PCR_ERR_IO = -6
 
 
 class RegResult(C.Structure):
@@ -84,6 +85,12 @@ class AlignResult(C.Structure):
     ]
 
 
+class PlyInfo(C.Structure):
+    """pcr_ply_info"""
+    _fields_ = [("n_vertex", C.c_int64), ("data_offset", C.c_int64), ("format", C.c_int32), ("has_normals", C.c_int32),
+                ("has_colors", C.c_int32), ("n_props", C.c_int32), ("vertex_stride", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/pcr.h declares (tests/test_capi_exports.py checks the list against the header)
 EXPORTS = [
     "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_set_stream", "pcr_version", "pcr_launch_count",
@@ -95,6 +102,7 @@ EXPORTS = [
     "pcr_ransac_step", "pcr_inlier_count",
     "pcr_icp_point_to_plane",
     "pcr_align_default_params", "pcr_align", "pcr_align_host",
+    "pcr_ply_probe", "pcr_ply_read", "pcr_ply_write",
 ]
 
 _lib = None

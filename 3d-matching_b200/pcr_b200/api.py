@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .engine import get_engine
-from .plyio import read_ply
+from .plyio import read_ply_xyzw
 
 
 def _load(x):
@@ -23,10 +23,10 @@ def _load(x):
             raise FileNotFoundError(f"Ply file not found: {p}")
         if p.suffix.lower() != ".ply":
             raise TypeError(f"File is not a ply file: {p}")
-        pts, _ = read_ply(p)
-        if len(pts) == 0:
+        xyzw, _ = read_ply_xyzw(p)  # native reader: file -> pinned packed float4 (one H2D copy, no pack kernel)
+        if len(xyzw) == 0:
             raise ValueError(f"Point cloud is empty: {p}")
-        return pts
+        return xyzw
     return x
 
 
@@ -44,7 +44,8 @@ def align(source, target, voxel_size: float, *, ransac_iteration: int = 100000, 
     p.icp_rel_rmse = float(relative_rmse)
     p.source_normals = int(bool(source_normals))
     s, t = _load(source), _load(target)
-    if isinstance(s, torch.Tensor) and s.is_cuda or isinstance(t, torch.Tensor) and t.is_cuda:
+    packed = lambda a: isinstance(a, torch.Tensor) and (a.is_cuda or a.shape[-1] == 4)
+    if packed(s) or packed(t):
         res = eng.align_device(eng.pack(s), eng.pack(t), p)
     else:
         s = s.cpu().numpy() if isinstance(s, torch.Tensor) else np.asarray(s)

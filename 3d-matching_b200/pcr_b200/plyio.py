@@ -1,78 +1,108 @@
-"""Minimal PLY reader/writer (replaces o3d.io.read_point_cloud at src/ply/ply.py:80 for the formats the
-reference produces: its converter writes ASCII PLY, convert_stl-ply.py:8).  ASCII and binary_little_endian,
-vertex properties x y z (float/double) and optional nx ny nz; other properties are skipped."""
+"""PLY reader/writer: ctypes binding of the native pcr_ply_* exports (include/pcr.h, csrc/pcr_ply.cu).
+
+Replaces o3d.io.read_point_cloud at src/ply/ply.py:80 (and o3d.io.write_point_cloud, trim_ply.py:40) for the formats
+the reference produces and consumes: ASCII (its converter's output, convert_stl-ply.py:8), binary_little_endian and
+binary_big_endian; vertex properties x y z of any scalar type, optional nx ny nz; other properties and elements are
+skipped.  `read_ply_xyzw` decodes straight into the packed float4 layout of the device kernels, into pinned memory
+when a GPU is present, so a file reaches HBM with one copy and no pack kernel.
+"""
 from __future__ import annotations
+
+import ctypes as C
+import os
 
 import numpy as np
 
-_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
-          "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
-          "double": "f8", "float64": "f8"}
+from . import _capi
+
+_ERR_CAP = 512
 
 
-def read_ply(path):
-    """Returns (points (n,3) float64, normals (n,3) float64 or None)."""
-    with open(path, "rb") as f:
-        if f.readline().strip() != b"ply":
-            raise ValueError(f"not a PLY file: {path}")
-        fmt = None
-        n_vertex = 0
-        props = []
-        in_vertex = False
-        while True:
-            line = f.readline()
-            if not line:
-                raise ValueError("unexpected end of PLY header")
-            tok = line.decode("ascii", "replace").split()
-            if not tok:
-                continue
-            if tok[0] == "format":
-                fmt = tok[1]
-            elif tok[0] == "element":
-                in_vertex = tok[1] == "vertex"
-                if in_vertex:
-                    n_vertex = int(tok[2])
-            elif tok[0] == "property" and in_vertex:
-                if tok[1] == "list":
-                    raise ValueError("list properties on vertices are not supported")
-                props.append((tok[2], _TYPES[tok[1]]))
-            elif tok[0] == "end_header":
-                break
-        names = [p[0] for p in props]
-        if not all(k in names for k in ("x", "y", "z")):
-            raise ValueError("PLY vertex element lacks x/y/z")
-        if n_vertex == 0:
-            return np.zeros((0, 3)), None
-        if fmt == "ascii":
-            data = np.loadtxt(f, dtype=np.float64, max_rows=n_vertex, ndmin=2)
-            cols = {n: data[:, i] for i, n in enumerate(names)}
-        elif fmt in ("binary_little_endian", "binary_big_endian"):
-            e = "<" if fmt == "binary_little_endian" else ">"
-            dt = np.dtype([(n, e + t) for n, t in props])
-            rec = np.frombuffer(f.read(dt.itemsize * n_vertex), dtype=dt, count=n_vertex)
-            cols = {n: rec[n].astype(np.float64) for n in names}
-        else:
-            raise ValueError(f"unsupported PLY format {fmt}")
-    pts = np.stack([cols["x"], cols["y"], cols["z"]], axis=1)
-    nrm = None
-    if all(k in cols for k in ("nx", "ny", "nz")):
-        nrm = np.stack([cols["nx"], cols["ny"], cols["nz"]], axis=1)
-    return pts, nrm
+def _raise(rc: int, err, path) -> None:
+    msg = err.value.decode("utf-8", "replace") or f"libpcr_b200 error {rc}"
+    if rc == _capi.PCR_ERR_IO:
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"Ply file not found: {path}")
+        raise OSError(f"{path}: {msg}")
+    if rc == _capi.PCR_ERR_OOM:
+        raise MemoryError(msg)
+    raise ValueError(f"{path}: {msg}")
 
 
-def write_ply(path, points, normals=None, binary=True):
-    points = np.asarray(points, np.float32)
-    n = len(points)
-    has_n = normals is not None
-    hdr = ["ply", "format binary_little_endian 1.0" if binary else "format ascii 1.0", f"element vertex {n}",
-           "property float x", "property float y", "property float z"]
-    if has_n:
-        hdr += ["property float nx", "property float ny", "property float nz"]
-    hdr.append("end_header")
-    data = points if not has_n else np.concatenate([points, np.asarray(normals, np.float32)], axis=1)
-    with open(path, "wb") as f:
-        f.write(("\n".join(hdr) + "\n").encode("ascii"))
-        if binary:
-            f.write(np.ascontiguousarray(data, "<f4").tobytes())
-        else:
-            np.savetxt(f, data, fmt="%.9g")
+def probe_ply(path) -> _capi.PlyInfo:
+    """Header only: vertex count, format, whether normals / colours are present."""
+    lib = _capi.load()
+    info, err = _capi.PlyInfo(), C.create_string_buffer(_ERR_CAP)
+    rc = lib.pcr_ply_probe(os.fsencode(path), C.byref(info), err, C.c_int(_ERR_CAP))
+    if rc != 0:
+        _raise(rc, err, path)
+    return info
+
+
+def _read(path, xyzw, nrm, xyz64, n, threads):
+    lib = _capi.load()
+    info, err = _capi.PlyInfo(), C.create_string_buffer(_ERR_CAP)
+    ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+    rc = lib.pcr_ply_read(os.fsencode(path), C.c_int64(n), ptr(xyzw), ptr(nrm), ptr(xyz64), C.c_int(threads),
+                          C.byref(info), err, C.c_int(_ERR_CAP))
+    if rc != 0:
+        _raise(rc, err, path)
+    return info
+
+
+def read_ply(path, threads: int = 0):
+    """Returns (points (n,3) float64, normals (n,3) float64 or None) — the values Open3D's containers would hold."""
+    info = probe_ply(path)
+    n = int(info.n_vertex)
+    pts = np.empty((n, 3), np.float64)
+    nrm4 = np.empty((n, 4), np.float32) if info.has_normals else None
+    if n:
+        _read(path, None, nrm4, pts, n, threads)
+    return pts, (nrm4[:, :3].astype(np.float64) if nrm4 is not None else None)
+
+
+def read_ply_xyzw(path, pin: bool | None = None, with_normals: bool = False, threads: int = 0):
+    """Returns (xyzw, normals_xyzw or None): (n,4) fp32 HOST torch tensors in the packed device layout (w = 0, points
+    quantised to fp32 — rule D1).  pin=None pins the memory when CUDA is available."""
+    import torch
+    info = probe_ply(path)
+    n = int(info.n_vertex)
+    if pin is None:
+        pin = torch.cuda.is_available()
+    xyzw = torch.empty((n, 4), dtype=torch.float32, pin_memory=bool(pin and n))
+    nrm = torch.empty((n, 4), dtype=torch.float32, pin_memory=bool(pin and n)) if (with_normals and info.has_normals) else None
+    if n:
+        _read(path, xyzw.numpy(), nrm.numpy() if nrm is not None else None, None, n, threads)
+    return xyzw, nrm
+
+
+def write_ply(path, points, normals=None, binary: bool = True, colors=None) -> None:
+    """points (n,3) or packed (n,4); normals likewise; colors (n,3) uint8, or floats in [0,1] as Open3D keeps them."""
+    def pack4(a):
+        a = np.asarray(a, np.float32)
+        if a.ndim != 2 or a.shape[1] not in (3, 4):
+            raise ValueError(f"expected an (n,3) array, got {a.shape}")
+        if a.shape[1] == 4:
+            return np.ascontiguousarray(a)
+        out = np.zeros((len(a), 4), np.float32)
+        out[:, :3] = a
+        return out
+    p4 = pack4(points)
+    n4 = pack4(normals) if normals is not None else None
+    rgb = None
+    if colors is not None:
+        c = np.asarray(colors)
+        if c.dtype != np.uint8:
+            c = np.clip(np.rint(np.asarray(c, np.float64) * 255.0), 0, 255).astype(np.uint8)
+        rgb = np.ascontiguousarray(c.reshape(-1, 3))
+        if len(rgb) != len(p4):
+            raise ValueError("colors and points differ in length")
+    if n4 is not None and len(n4) != len(p4):
+        raise ValueError("normals and points differ in length")
+    lib = _capi.load()
+    err = C.create_string_buffer(_ERR_CAP)
+    ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+    rc = lib.pcr_ply_write(os.fsencode(path), ptr(p4), C.c_int64(len(p4)), ptr(n4), ptr(rgb), C.c_int(int(binary)),
+                           err, C.c_int(_ERR_CAP))
+    if rc != 0:
+        _raise(rc, err, path)

@@ -20,7 +20,7 @@ import numpy as np
 
 from pcr_b200.containers import Feature, PointCloud
 from pcr_b200.engine import get_engine
-from pcr_b200.plyio import read_ply
+from pcr_b200.plyio import read_ply_xyzw
 
 
 class Ply:
@@ -33,7 +33,7 @@ class Ply:
                 raise FileNotFoundError(f"Ply file not found: {self.path}")
             if self.path.suffix.lower() != ".ply":
                 raise TypeError(f"File is not a ply file: {self.path}")
-            pts, _ = read_ply(self.path)
+            pts, _ = read_ply_xyzw(self.path)  # pcr_ply_read: pinned packed float4, replaces ply.py:80
             if len(pts) == 0:
                 raise ValueError(f"Point cloud is empty: {self.path}")
         else:

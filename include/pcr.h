@@ -41,7 +41,8 @@ typedef enum pcr_status {
     PCR_ERR_CUDA = -2,    /* CUDA runtime failure (RuntimeError) */
     PCR_ERR_OOM = -3,     /* device allocation failed (MemoryError) */
     PCR_ERR_BUSY = -4,    /* context used concurrently */
-    PCR_ERR_TOO_LARGE = -5 /* voxel/search grid would exceed the dense-grid cell budget */
+    PCR_ERR_TOO_LARGE = -5, /* voxel/search grid would exceed the dense-grid cell budget */
+    PCR_ERR_IO = -6         /* pcr_ply_*: file missing / unreadable / short write (OSError) */
 } pcr_status;
 
 typedef struct pcr_ctx pcr_ctx;
@@ -209,6 +210,35 @@ PCR_API int pcr_align(pcr_ctx *ctx, const float *src_xyzw_dev, int ns, const flo
 /* host inputs: (n,3) fp32 host arrays; H2D copies, the full path and the D2H of the result are inside */
 PCR_API int pcr_align_host(pcr_ctx *ctx, const float *src_xyz_host, int ns, const float *tgt_xyz_host, int nt,
                            const pcr_align_params *p, pcr_align_result *result_host);
+
+/* ---- PLY files (host only; no context, no device work) ------------------------------------------------------
+ * Replaces o3d.io.read_point_cloud (src/ply/ply.py:80) and o3d.io.write_point_cloud (trim_ply.py:40; the
+ * reference's converter writes ASCII PLY, convert_stl-ply.py:8).  Formats: ascii, binary_little_endian,
+ * binary_big_endian; vertex properties x y z of any scalar type, optional nx ny nz; other vertex properties and
+ * other elements (faces) are skipped; list properties on the vertex element are PCR_ERR_INVALID.  A file without
+ * vertices reads as n_vertex = 0 (the mirror raises the reference's ValueError, src/ply/ply.py:81-84).
+ * Errors are returned as pcr_status plus a message in `err` (may be NULL).  The functions are thread-safe. */
+typedef struct pcr_ply_info {
+    int64_t n_vertex;
+    int64_t data_offset;   /* byte offset of the first element record */
+    int32_t format;        /* 0 ascii, 1 binary_little_endian, 2 binary_big_endian */
+    int32_t has_normals;   /* nx ny nz present */
+    int32_t has_colors;    /* red green blue present */
+    int32_t n_props;       /* properties of the vertex element */
+    int32_t vertex_stride; /* bytes per vertex record (binary formats; 0 for ascii) */
+    int32_t reserved;
+} pcr_ply_info;
+PCR_API int pcr_ply_probe(const char *path, pcr_ply_info *info, char *err, int err_cap);
+/* Decodes the vertices into caller-provided HOST buffers (each may be NULL): xyzw_host (n,4) fp32 packed float4
+ * with w = 0 — the device layout, so pinned memory goes to the GPU with one cudaMemcpy; normals_xyzw_host (n,4)
+ * fp32, written only when the file has normals (see info->has_normals); xyz64_host (n,3) fp64, the values before
+ * the fp32 quantisation of rule D1.  n_cap = capacity of the buffers in vertices.  threads <= 0: automatic. */
+PCR_API int pcr_ply_read(const char *path, int64_t n_cap, float *xyzw_host, float *normals_xyzw_host,
+                         double *xyz64_host, int threads, pcr_ply_info *info, char *err, int err_cap);
+/* Writes n vertices from packed float4 host arrays; normals (n,4) fp32 and rgb (n,3) uint8 are optional.
+ * binary != 0: binary_little_endian; 0: ascii with the shortest decimal text that reads back to the same fp32. */
+PCR_API int pcr_ply_write(const char *path, const float *xyzw_host, int64_t n, const float *normals_xyzw_host,
+                          const unsigned char *rgb_host, int binary, char *err, int err_cap);
 
 #ifdef __cplusplus
 }

@@ -282,3 +282,49 @@ def test_align_deterministic_under_overlap_and_threads(eng):
     for t in ths:
         t.join()
     assert all(len(o) == 10 and all(x == base[0] for x in o) for o in outs)
+
+
+def test_main_pipeline_and_headless_draw(tmp_path, eng, capsys):
+    """src/main.py:24-39 on the engine: Ply x2 -> global_registration -> draw -> refine_registration -> draw, from PLY
+    files through the native reader; the 'viewer' writes a coloured PLY + JSON per call."""
+    import importlib.util
+    import json
+    import os
+    from pcr_b200.plyio import probe_ply, read_ply, write_ply
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("b200_main", os.path.join(root, "3d-matching_b200", "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    v = 0.005
+    src, tgt, T_true = synth.make_pair(12000, v, 77)
+    write_ply(tmp_path / "sample.ply", src, binary=False)
+    write_ply(tmp_path / "target.ply", tgt)
+    out = tmp_path / "viz"
+    rc = mod.main(["--source", str(tmp_path / "sample.ply"), "--target", str(tmp_path / "target.ply"), "--voxel-size", str(v),
+                   "--ransac-iterations", "50000", "--noise-sigma", "0", "--export-dir", str(out)])
+    assert rc == 0
+    text = capsys.readouterr().out
+    assert "transformation (ICP):" in text and "fitness" in text
+    files = sorted(p.name for p in out.iterdir())
+    assert len(files) == 4 and files[0].endswith(".json") and files[1].endswith(".ply")
+    plys = sorted(out.glob("*.ply"))
+    meta = json.loads(plys[-1].with_suffix(".json").read_text())
+    T = np.array(meta["transformation"])
+    assert np.abs(T[:3, :3] - T_true[:3, :3]).max() < 5e-3 and meta["fitness"] > 0.9
+    info = probe_ply(plys[-1])
+    assert info.has_colors == 1 and info.n_vertex == meta["n_source"] + meta["n_target"]
+    # the first n_source vertices are the down-sampled source moved by T; the rest is the down-sampled target, unmoved
+    from ply import Ply
+    s, t = Ply(tmp_path / "sample.ply", v, noise_sigma=0.0), Ply(tmp_path / "target.ply", v, noise_sigma=0.0)
+    pts, _ = read_ply(plys[-1])
+    ns = meta["n_source"]
+    assert ns == len(s.pcd_down.points) and meta["n_target"] == len(t.pcd_down.points)
+    assert np.array_equal(pts[ns:], t.pcd_down.points)
+    assert np.abs(pts[:ns] - (s.pcd_down.points @ T[:3, :3].T + T[:3, 3])).max() < 1e-6
+    # missing input: exit code 1 and a message, as Ply raises FileNotFoundError (src/ply/ply.py:46-47)
+    assert mod.main(["--source", str(tmp_path / "nope.ply"), "--target", str(tmp_path / "target.ply")]) == 1
+    # align() takes the same files through the native reader
+    from pcr_b200 import align
+    Ta, fit, rmse = align(tmp_path / "sample.ply", tmp_path / "target.ply", v, ransac_iteration=50000)
+    Tb, fitb, rmseb = align(src, tgt, v, ransac_iteration=50000)
+    assert np.array_equal(Ta, Tb) and fit == fitb and rmse == rmseb

@@ -161,3 +161,23 @@ def test_benchmark_cli_arguments_match_the_reference():
         line = next(ln for ln in src.splitlines() if f'"{flag}"' in ln)
         assert f"default={default}" in line, line
     assert importlib.util.find_spec("torch") is not None
+
+
+def test_main_py_imports_resolve_without_the_reference(tmp_path):
+    """src/main.py:13-17 imports matcher, ply, utils.setup_logging and visualization as top-level packages; with
+    3d-matching_b200/ on the path they all resolve to this engine."""
+    import importlib
+    import logging
+    for name in ("matcher.icp", "matcher.ransac", "ply", "utils.setup_logging", "visualization.draw_registration_result"):
+        m = importlib.import_module(name)
+        assert "3d-matching_b200" in m.__file__, (name, m.__file__)
+    from utils.setup_logging import setup_logging
+    log = setup_logging("pcr.test.logger")
+    assert log.level == logging.INFO and setup_logging("pcr.test.logger") is log and len(log.handlers) <= 1
+    from visualization.draw_registration_result import SOURCE_COLOR, TARGET_COLOR, _as_matrix
+    assert SOURCE_COLOR == (1.0, 0.706, 0.0) and TARGET_COLOR == (0.0, 0.651, 0.929)  # draw_registration_result.py:37-38
+    from pcr_b200.containers import RegistrationResult
+    T = np.arange(16.0).reshape(4, 4)
+    assert np.array_equal(_as_matrix(RegistrationResult(T)), T) and np.array_equal(_as_matrix(T.tolist()), T)
+    with pytest.raises(ValueError):
+        _as_matrix(np.eye(3))
