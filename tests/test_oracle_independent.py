@@ -13,6 +13,7 @@ arithmetic lives in the absent wheel:
 import math
 
 import numpy as np
+import pytest
 
 import np_ref
 from pcr_b200 import synth
@@ -164,3 +165,81 @@ def test_icp_step_matches_numpy_gauss_newton(orc):
         assert abs(got.inlier_count - int(m.sum())) <= 1
         assert abs(got.fitness - m.mean()) <= 1.0 / len(src)
         assert abs(got.inlier_rmse - math.sqrt(d2[m].astype(np.float64).sum() / m.sum())) < 1e-6 * max_dist
+
+
+def py_philox4x32_10(counter: int, key: int):
+    """Philox4x32-10 (Salmon et al., SC'11) on Python integers: 128-bit counter, 64-bit key -> four 32-bit words."""
+    M = 0xFFFFFFFF
+    c = [(counter >> (32 * i)) & M for i in range(4)]
+    k0, k1 = key & M, (key >> 32) & M
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k0, p1 & M, (p0 >> 32) ^ c[3] ^ k1, p0 & M]
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return c
+
+
+def np_umeyama(X, Y):
+    """Eigen::umeyama(X, Y, with_scaling=false) as published: Sigma = Yc^T Xc / n, U S V^T = svd(Sigma),
+    S = diag(1, 1, sign(det U det V)), R = U S V^T, t = mu_y - R mu_x."""
+    mx, my = X.mean(0), Y.mean(0)
+    sigma = (Y - my).T @ (X - mx) / len(X)
+    U, _, Vt = np.linalg.svd(sigma)
+    S = np.diag([1.0, 1.0, 1.0 if np.linalg.det(U) * np.linalg.det(Vt) > 0 else -1.0])
+    T = np.eye(4)
+    T[:3, :3] = U @ S @ Vt
+    T[:3, 3] = my - T[:3, :3] @ mx
+    return T
+
+
+@pytest.mark.parametrize("conf,max_iter", [(0.999, 4000), (1.0, 1500)])
+def test_ransac_loop_matches_sequential_numpy_restatement(orc, conf, max_iter):
+    """A.6, single-threaded: Philox-keyed 3-samples with replacement, edge-length(0.9) and distance checkers, Umeyama,
+    full NN validation of the survivors, best = (more inliers, then smaller RMSE), est_k = ln(1-conf)/ln(1-ratio^3)."""
+    v = 0.05
+    src_full, tgt_full, T_true = synth.make_pair(4000, v, 61)
+    S, G = orc.preprocess(src_full, v, full_normals=False), orc.preprocess(tgt_full, v, full_normals=False)
+    src, tgt = S.pcd_down, G.pcd_down
+    corr = orc.match_features(S.pcd_fpfh, G.pcd_fpfh, True)
+    c, max_dist, seed = len(corr), 1.5 * v, 5
+    assert 30 < c and len(src) < 1500
+    s64, t64 = src.astype(np.float64), tgt.astype(np.float64)
+    est_k, best, evaluated, survivors = max_iter, None, 0, 0
+    h = 0
+    while h < max_iter and h < est_k:
+        r = py_philox4x32_10(h, seed)
+        ids = [(r[k] * c) >> 32 for k in range(3)]
+        X, Y = s64[corr[ids, 0]], t64[corr[ids, 1]]
+        h += 1
+        evaluated += 1
+        ok = True
+        for i in range(3):
+            for j in range(i + 1, 3):
+                ds, dt = np.linalg.norm(X[i] - X[j]), np.linalg.norm(Y[i] - Y[j])
+                ok &= not (ds < 0.9 * dt or dt < 0.9 * ds)
+        if not ok:
+            continue
+        T = np_umeyama(X, Y)
+        if not np.isfinite(T).all() or (np.linalg.norm(X @ T[:3, :3].T + T[:3, 3] - Y, axis=1) > max_dist).any():
+            continue
+        survivors += 1
+        j, d2 = np_ref.nn1(tgt, np_ref.transform_f32(T, src), max_dist)
+        m = j >= 0
+        cnt, sumd2 = int(m.sum()), float(d2[m].astype(np.float64).sum())
+        if best is None or cnt > best[0] or (cnt == best[0] and cnt > 0 and sumd2 < best[1]):
+            best = (cnt, sumd2, h - 1, T)
+            p = src[corr[:, 0]].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+            ratio = float((np.linalg.norm(p - t64[corr[:, 1]], axis=1) < max_dist).mean())
+            if 0.0 < ratio < 1.0 and conf < 1.0:  # confidence 1.0 consumes every iteration
+                est = math.log(1.0 - conf) / math.log(1.0 - ratio ** 3)
+                if 0.0 <= est < est_k:
+                    est_k = int(math.ceil(est))
+            elif ratio >= 1.0 and conf < 1.0:
+                est_k = 0
+    got = orc.ransac(src, tgt, corr, max_dist, max_iter, conf, seed)
+    assert best is not None and survivors >= (3 if conf < 1.0 else 100)
+    assert (got.best_hyp, got.hyp_evaluated, got.survivors, got.est_k) == (best[2], evaluated, survivors, est_k)
+    assert got.inlier_count == best[0]
+    assert np.abs(got.transformation - best[3]).max() < 1e-9
+    assert abs(got.inlier_rmse - math.sqrt(best[1] / best[0])) < 1e-9
+    assert got.fitness == best[0] / len(src)
