@@ -362,3 +362,40 @@ def test_tensor_core_matching_is_exact(orc, eng):
         assert np.array_equal(nn, ref)
         assert nn[7] == 50 and nn[300] == 600
         assert np.array_equal(eng.match_features(dfs, dft, True, 0.0).cpu().numpy(), orc.match_features(fs, ft, True, 0.0))
+
+
+def _degenerate_cases():
+    rng = np.random.default_rng(0)
+    v = 0.005
+    src, tgt, _ = synth.make_pair(3000, v, 9)
+    line = lambda n, off: (np.stack([np.linspace(0, 1, n)] * 3, 1) + off).astype(np.float32)  # noqa: E731
+    plane = lambda n: np.concatenate([rng.random((n, 2)), np.zeros((n, 1))], 1).astype(np.float32)  # noqa: E731
+    return [
+        ("three_points", rng.random((3, 3)).astype(np.float32), rng.random((3, 3)).astype(np.float32), 0.1),
+        ("single_point", np.ones((1, 3), np.float32), 2 * np.ones((1, 3), np.float32), 0.1),
+        ("all_identical", np.ones((500, 3), np.float32), np.ones((400, 3), np.float32), 0.05),
+        ("one_voxel", src, tgt, 10.0),                      # both clouds collapse to one point: no correspondences
+        ("disjoint", src, (tgt + 100.0).astype(np.float32), v),  # RANSAC finds a transform, ICP has no pairs
+        ("collinear", line(800, 0.0), line(700, 0.001), 0.01),  # singular normal equations
+        ("coplanar", plane(2000), plane(2100), 0.02),
+        ("tiny_vs_big", src[:7], tgt, v),
+    ]
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_align_degenerate_inputs_follow_the_oracle(orc, eng, case):
+    """Whole-pipeline soft failures (SURVEY §8b error conventions; the shapes of test_ransac_crash.py:27-79 pushed through
+    align()): nothing raises, fewer than three correspondences give the identity with fitness 0 from RANSAC, singular
+    or empty ICP systems leave the transform finite — and every number equals the oracle's."""
+    from pcr_b200 import align
+    name, s, t, v = _degenerate_cases()[case]
+    T, fit, rmse, info = align(s, t, v, ransac_iteration=2000, seed=0, return_info=True)
+    S, G = orc.preprocess(s, v), orc.preprocess(t, v)
+    ro = orc.global_registration(S, G, v, 2000, 0.999, 0)
+    io = orc.refine_registration(S, G, ro.transformation, v)
+    assert np.isfinite(T).all(), name
+    assert (info.n_src_down, info.n_tgt_down) == (len(S.pcd_down), len(G.pcd_down)), name
+    assert info.ransac.best_hyp == ro.best_hyp and info.ransac.fitness == ro.fitness, name
+    assert np.array_equal(np.array(info.ransac.transformation).reshape(4, 4), ro.transformation), name
+    assert np.array_equal(T, io.transformation) and fit == io.fitness and rmse == io.inlier_rmse, name
+    assert info.icp.iterations == io.iterations, name
