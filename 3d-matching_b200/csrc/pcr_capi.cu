@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include "pcr_common.cuh"
+#include <thread>
 
 typedef unsigned long long u64;
 
@@ -369,6 +370,56 @@ int pcr_align_host(pcr_ctx *ctx, const float *src_xyz, int ns, const float *tgt_
     PCR_TRY(pcr_pack_impl(ctx, s3, ns, s4));
     PCR_TRY(pcr_pack_impl(ctx, t3, nt, t4));
     return align_device(ctx, s4, ns, t4, nt, p, result);
+}
+
+int pcr_align_files(pcr_ctx *ctx, const char *src_path, const char *tgt_path, const pcr_align_params *p,
+                    pcr_align_result *result) {
+    PCR_ENTER();
+    PCR_ARG(src_path && tgt_path && p && result);
+    pcr_ply_info is, it;
+    char err_s[256], err_t[256];
+    int rc = pcr_ply_probe(src_path, &is, err_s, (int)sizeof err_s);
+    if (rc != PCR_OK) return pcr_fail(ctx, rc, "%s: %s", src_path, err_s);
+    rc = pcr_ply_probe(tgt_path, &it, err_t, (int)sizeof err_t);
+    if (rc != PCR_OK) return pcr_fail(ctx, rc, "%s: %s", tgt_path, err_t);
+    if (is.n_vertex == 0 || it.n_vertex == 0) return pcr_fail(ctx, PCR_ERR_INVALID, "Point cloud is empty");
+    PCR_ARG(is.n_vertex <= 0x7fffffff && it.n_vertex <= 0x7fffffff);
+    const int ns = (int)is.n_vertex, nt = (int)it.n_vertex;
+    const size_t need = sizeof(float4) * ((size_t)ns + (size_t)nt);
+    if (ctx->stage_bytes < need) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        const size_t cap = need + need / 4;
+        if (cudaMallocHost(&ctx->stage, cap) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->stage = nullptr;
+            return pcr_fail(ctx, PCR_ERR_OOM, "cannot pin %zu bytes of host memory for the file staging buffer", cap);
+        }
+        ctx->stage_bytes = cap;
+    }
+    float *hs = (float *)ctx->stage, *ht = hs + 4 * (size_t)ns;
+    // the two files are decoded concurrently (each decode is itself multi-threaded for large files)
+    int rc_t = PCR_OK;
+    bool threaded = false;
+    std::thread th;
+    try {
+        th = std::thread([&] { rc_t = pcr_ply_read(tgt_path, nt, ht, nullptr, nullptr, 0, nullptr, err_t, (int)sizeof err_t); });
+        threaded = true;
+    } catch (...) {
+    }
+    rc = pcr_ply_read(src_path, ns, hs, nullptr, nullptr, 0, nullptr, err_s, (int)sizeof err_s);
+    if (threaded) th.join();
+    else rc_t = pcr_ply_read(tgt_path, nt, ht, nullptr, nullptr, 0, nullptr, err_t, (int)sizeof err_t);
+    if (rc != PCR_OK) return pcr_fail(ctx, rc, "%s: %s", src_path, err_s);
+    if (rc_t != PCR_OK) return pcr_fail(ctx, rc_t, "%s: %s", tgt_path, err_t);
+    PCR_ALLOC(s4, float4, (size_t)ns);
+    PCR_ALLOC(t4, float4, (size_t)nt);
+    PCR_CUDA(cudaMemcpyAsync(s4, hs, sizeof(float4) * (size_t)ns, cudaMemcpyHostToDevice, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(t4, ht, sizeof(float4) * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    rc = align_device(ctx, s4, ns, t4, nt, p, result);
+    if (rc != PCR_OK) cudaStreamSynchronize(ctx->stream);  // the staging buffer is reused by the next call
+    return rc;
 }
 
 }  // extern "C"

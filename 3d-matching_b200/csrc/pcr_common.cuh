@@ -85,6 +85,9 @@ struct pcr_ctx {
     // pinned host staging for small result records
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // pinned staging for file input (pcr_align_files): grow-only, freed at destroy
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
     bool busy = false;
     // bounding boxes already reduced during the current exported call, keyed by (pointer, n); cleared on entry
     struct BoundsEntry { const void *ptr; int n; float lo[3], hi[3]; };

@@ -212,6 +212,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
     delete ctx;

@@ -101,7 +101,7 @@ EXPORTS = [
     "pcr_ransac", "pcr_ransac_wave", "pcr_ransac_session_begin", "pcr_ransac_session_end", "pcr_ransac_scan", "pcr_ransac_k_d",
     "pcr_ransac_step", "pcr_inlier_count",
     "pcr_icp_point_to_plane",
-    "pcr_align_default_params", "pcr_align", "pcr_align_host",
+    "pcr_align_default_params", "pcr_align", "pcr_align_host", "pcr_align_files",
     "pcr_ply_probe", "pcr_ply_read", "pcr_ply_write",
 ]
 
@@ -144,4 +144,6 @@ def check(lib, ctx, rc: int) -> None:
         raise ValueError(msg or "invalid argument")
     if rc == PCR_ERR_OOM:
         raise MemoryError(msg or "device out of memory")
+    if rc == PCR_ERR_IO:
+        raise OSError(msg or "file I/O error")
     raise PcrError(f"libpcr_b200 error {rc}: {msg}")

@@ -2,7 +2,7 @@
 
 Runs the reference's whole pipeline — Ply preprocessing (src/ply/ply.py:87-135), global_registration
 (src/matcher/ransac.py:20-59), refine_registration (src/matcher/icp.py:17-48) — as ONE call into the C ABI
-(pcr_align_host for host arrays / PLY paths, pcr_align for device tensors).
+(pcr_align_files for two PLY paths, pcr_align_host for host arrays, pcr_align for device tensors).
 """
 from __future__ import annotations
 
@@ -16,13 +16,23 @@ from .engine import get_engine
 from .plyio import read_ply_xyzw
 
 
+def _is_path(x) -> bool:
+    return isinstance(x, (str, os.PathLike, Path))
+
+
+def _check_path(x) -> Path:
+    """The reference's input validation (src/ply/ply.py:46-51)."""
+    p = Path(x)
+    if not p.exists():
+        raise FileNotFoundError(f"Ply file not found: {p}")
+    if p.suffix.lower() != ".ply":
+        raise TypeError(f"File is not a ply file: {p}")
+    return p
+
+
 def _load(x):
-    if isinstance(x, (str, os.PathLike, Path)):
-        p = Path(x)
-        if not p.exists():
-            raise FileNotFoundError(f"Ply file not found: {p}")
-        if p.suffix.lower() != ".ply":
-            raise TypeError(f"File is not a ply file: {p}")
+    if _is_path(x):
+        p = _check_path(x)
         xyzw, _ = read_ply_xyzw(p)  # native reader: file -> pinned packed float4 (one H2D copy, no pack kernel)
         if len(xyzw) == 0:
             raise ValueError(f"Point cloud is empty: {p}")
@@ -43,6 +53,11 @@ def align(source, target, voxel_size: float, *, ransac_iteration: int = 100000, 
     p.icp_rel_fitness = float(relative_fitness)
     p.icp_rel_rmse = float(relative_rmse)
     p.source_normals = int(bool(source_normals))
+    if _is_path(source) and _is_path(target):
+        # both clouds come from files: one C call decodes them concurrently into pinned staging and aligns
+        res = eng.align_files(_check_path(source), _check_path(target), p)
+        T = np.array(res.icp.transformation, np.float64).reshape(4, 4)
+        return (T, res.icp.fitness, res.icp.inlier_rmse, res) if return_info else (T, res.icp.fitness, res.icp.inlier_rmse)
     s, t = _load(source), _load(target)
     packed = lambda a: isinstance(a, torch.Tensor) and (a.is_cuda or a.shape[-1] == 4)
     if packed(s) or packed(t):

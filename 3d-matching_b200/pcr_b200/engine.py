@@ -353,6 +353,16 @@ class Engine:
                                                 C.byref(res)))
         return res
 
+    def align_files(self, src_path, tgt_path, params: _capi.AlignParams) -> _capi.AlignResult:
+        """PLY paths in, result out — one C call (pcr_align_files: concurrent native decode into pinned staging)."""
+        import os
+        res = _capi.AlignResult()
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_align_files(self.ctx, os.fsencode(src_path), os.fsencode(tgt_path), C.byref(params),
+                                                 C.byref(res)))
+        return res
+
 
 _default_engines: dict[int, Engine] = {}
 

@@ -211,6 +211,12 @@ PCR_API int pcr_align(pcr_ctx *ctx, const float *src_xyzw_dev, int ns, const flo
 PCR_API int pcr_align_host(pcr_ctx *ctx, const float *src_xyz_host, int ns, const float *tgt_xyz_host, int nt,
                            const pcr_align_params *p, pcr_align_result *result_host);
 
+/* PLY paths (src/main.py:26-31 hands paths to Ply()): both files are decoded concurrently by pcr_ply_read (below)
+ * into the context's pinned staging buffer, copied to the device once each, and aligned; the timed region of a caller
+ * therefore covers file -> result.  File errors return the pcr_ply_* status (PCR_ERR_IO / PCR_ERR_INVALID). */
+PCR_API int pcr_align_files(pcr_ctx *ctx, const char *src_path, const char *tgt_path, const pcr_align_params *p,
+                            pcr_align_result *result_host);
+
 /* ---- PLY files (host only; no context, no device work) ------------------------------------------------------
  * Replaces o3d.io.read_point_cloud (src/ply/ply.py:80) and o3d.io.write_point_cloud (trim_ply.py:40; the
  * reference's converter writes ASCII PLY, convert_stl-ply.py:8).  Formats: ascii, binary_little_endian,

@@ -328,3 +328,19 @@ def test_main_pipeline_and_headless_draw(tmp_path, eng, capsys):
     Ta, fit, rmse = align(tmp_path / "sample.ply", tmp_path / "target.ply", v, ransac_iteration=50000)
     Tb, fitb, rmseb = align(src, tgt, v, ransac_iteration=50000)
     assert np.array_equal(Ta, Tb) and fit == fitb and rmse == rmseb
+    # pcr_align_files error paths: a truncated file is a ValueError naming the file, an empty cloud the reference's
+    # "Point cloud is empty" (src/ply/ply.py:81-84); the context stays usable afterwards
+    bad = tmp_path / "bad.ply"
+    bad.write_bytes((tmp_path / "target.ply").read_bytes()[:-40])
+    with pytest.raises(ValueError, match="truncated"):
+        align(tmp_path / "sample.ply", bad, v)
+    write_ply(tmp_path / "empty.ply", src[:0])
+    with pytest.raises(ValueError, match="empty"):
+        align(tmp_path / "empty.ply", tmp_path / "target.ply", v)
+    with pytest.raises(TypeError):
+        align(tmp_path / "sample.ply", __file__, v)
+    Tc, fitc, _ = align(tmp_path / "sample.ply", tmp_path / "target.ply", v, ransac_iteration=50000)
+    assert np.array_equal(Tc, Ta) and fitc == fit
+    # one path + one array still works (the file goes through read_ply_xyzw)
+    Td, fitd, _ = align(tmp_path / "sample.ply", tgt, v, ransac_iteration=50000)
+    assert np.array_equal(Td, Ta) and fitd == fit
