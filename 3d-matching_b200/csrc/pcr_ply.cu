@@ -288,6 +288,8 @@ size_t binary_vertex_offset(const Mapped &f, const Header &h) {
     for (int e = 0; e < h.vertex; ++e) {
         const Element &el = h.elements[e];
         if (!el.has_list) {
+            if (off > f.n || (el.stride > 0 && (size_t)el.count > (f.n - off) / (size_t)el.stride))
+                fail(PCR_ERR_INVALID, "PLY file is truncated");
             off += (size_t)el.stride * (size_t)el.count;
             continue;
         }

@@ -246,3 +246,51 @@ def test_ascii_reader_throughput_is_reported(tmp_path, capsys):
     assert same(a[:, :3], b.astype(np.float32))
     with capsys.disabled():
         print(f"\n[ply] 100k ASCII vertices: native {1e3 * (t1 - t0):.1f} ms, numpy.loadtxt {1e3 * (t2 - t1):.1f} ms")
+
+
+def test_reader_survives_mutated_files(tmp_path):
+    """Robustness: truncations, byte flips and spliced garbage in valid files either decode or return an error code —
+    the mapped input is never read out of bounds and nothing throws across the C ABI (a crash would take pytest down)."""
+    import ctypes as C
+    lib = _capi.load()
+    rng = np.random.default_rng(1234)
+    n = 300
+    pts, nrm = cloud(n, 1).astype(np.float32), cloud(n, 2).astype(np.float32)
+    seeds = []
+    for binary in (True, False):
+        p = tmp_path / f"seed{int(binary)}.ply"
+        write_ply(p, pts, nrm, binary=binary, colors=np.zeros((n, 3), np.uint8))
+        seeds.append(p.read_bytes())
+    be = header("binary_big_endian", n, [("x", "double"), ("y", "short"), ("z", "float")],
+                extra_before="element cam 3\nproperty list uchar int k\nproperty float a\n")
+    seeds.append(be + bytes(rng.integers(0, 256, 3 * 9 + n * 14, dtype=np.uint8)))
+    buf = np.zeros((n + 8, 4), np.float32)
+    nbuf = np.zeros((n + 8, 4), np.float32)
+    err = C.create_string_buffer(256)
+    info = _capi.PlyInfo()
+    f = tmp_path / "m.ply"
+    outcomes = {0: 0, _capi.PCR_ERR_INVALID: 0}
+    for it in range(1500):
+        data = bytearray(seeds[it % len(seeds)])
+        kind = it % 5
+        if kind == 0:
+            data = data[: int(rng.integers(0, len(data)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 8))):
+                data[int(rng.integers(0, len(data)))] = int(rng.integers(0, 256))
+        elif kind == 2:  # flips confined to the header
+            hdr_end = data.find(b"end_header") + 11
+            for _ in range(int(rng.integers(1, 4))):
+                data[int(rng.integers(0, hdr_end))] = int(rng.integers(32, 127))
+        elif kind == 3:  # a count that no longer matches the body
+            data = data.replace(b"element vertex 300", b"element vertex %d" % int(rng.integers(0, 10**12)))
+        else:
+            a = int(rng.integers(0, len(data)))
+            data[a:a] = bytes(rng.integers(0, 256, int(rng.integers(1, 64)), dtype=np.uint8))
+        f.write_bytes(bytes(data))
+        rc = lib.pcr_ply_read(os.fsencode(f), C.c_int64(len(buf)), C.c_void_p(buf.ctypes.data), C.c_void_p(nbuf.ctypes.data),
+                              None, 0, C.byref(info), err, 256)
+        assert rc in (0, _capi.PCR_ERR_INVALID), (it, rc, err.value)
+        assert (rc == 0) or err.value, it
+        outcomes[rc] += 1
+    assert outcomes[0] > 50 and outcomes[_capi.PCR_ERR_INVALID] > 300, outcomes
