@@ -60,3 +60,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(d, f), errors="replace").read()
                 assert not bad.search(txt), os.path.join(d, f)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/pcr.h compiles as C11 (-pedantic) and a C program links libpcr_b200.so and calls the host-only exports
+    (PLY I/O, RANSAC replay, defaults) — the drop-in boundary is a C ABI, not a C++ one."""
+    import shutil
+    import subprocess
+    from pcr_b200 import _capi
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-L", libdir, "-lpcr_b200", f"-Wl,-rpath,{libdir}",
+           "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "scratch.ply")], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi_check ok" in r.stdout, r.stderr
