@@ -294,3 +294,41 @@ def test_reader_survives_mutated_files(tmp_path):
         assert (rc == 0) or err.value, it
         outcomes[rc] += 1
     assert outcomes[0] > 50 and outcomes[_capi.PCR_ERR_INVALID] > 300, outcomes
+
+
+def test_ascii_numbers_are_correctly_rounded(tmp_path):
+    """Every decimal form goes to the double Python's float() gives (correct rounding) — the exact fast path (<= 15
+    digits, |exponent| <= 22) and the general routine alike."""
+    rng = np.random.default_rng(7)
+    toks = []
+    for _ in range(6000):
+        kind = int(rng.integers(0, 8))
+        x = float(rng.standard_normal() * 10.0 ** int(rng.integers(-8, 9)))
+        if kind == 0:
+            toks.append("%.9g" % x)
+        elif kind == 1:
+            toks.append("%.17g" % x)                      # 17 digits: general routine
+        elif kind == 2:
+            toks.append("%.6f" % x)
+        elif kind == 3:
+            toks.append("%.3e" % x)
+        elif kind == 4:
+            toks.append("%d" % int(x))
+        elif kind == 5:
+            toks.append("%.15g" % x)                      # 15 digits: the edge of the fast path
+        elif kind == 6:
+            toks.append(("%.5f" % rng.standard_normal()) + "e%+d" % int(rng.integers(-30, 31)))  # exponents around +-22
+        else:
+            toks.append("%se%d" % (int(rng.integers(1, 10**15)), int(rng.integers(-40, 40))))
+    toks += ["0", "-0", "0.0", "-0.000", "000123.4500", ".5", "5.", "-.25", "1e22", "1e23", "1e-22", "1e-23",
+             "9007199254740993", "999999999999999", "1000000000000000", "4.9e-324", "1.7976931348623157e308", "1e400",
+             "123456789012345678901234567890", "0.1e1", "1E5", "+3.5"]
+    while len(toks) % 3:
+        toks.append("1")
+    p = tmp_path / "n.ply"
+    n = len(toks) // 3
+    body = "\n".join(" ".join(toks[3 * i: 3 * i + 3]) for i in range(n)) + "\n"
+    p.write_bytes(header("ascii", n, [(k, "double") for k in "xyz"]) + body.encode())
+    got = read_ply(p)[0].reshape(-1)
+    want = np.array([float(t) for t in toks])
+    assert got.tobytes() == want.tobytes(), [(t, g, w) for t, g, w in zip(toks, got, want) if not (g == w and np.signbit(g) == np.signbit(w))][:5]
