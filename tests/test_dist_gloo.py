@@ -103,3 +103,78 @@ def test_two_ranks_reproduce_the_sequential_result(conf, max_iter, fixed_cap):
         assert (best, cnt, sq, est_k, ev) == (want.best_hyp, want.inlier_count, want.sum_d2_fixed, want.est_k, want.hyp_evaluated)
         assert np.array_equal(np.array(T).reshape(4, 4), want.transformation)
         assert fit == want.fitness and rmse == want.inlier_rmse
+
+
+class _OracleEngine:
+    """Duck-typed stand-in for pcr_b200.engine.Engine in align_batch: `tdev` and `align_device(src, tgt, params)`.
+    The alignment itself is the CPU oracle's (allowed in tests); what is under test is the pair -> rank mapping, the
+    ragged last round (5 pairs on 2 ranks) and the final all-gather."""
+
+    def __init__(self, orc, v):
+        import torch
+        self.orc, self.v, self.tdev = orc, v, torch.device("cpu")
+        self.calls = []
+
+    def align_device(self, src, tgt, params):
+        from types import SimpleNamespace
+        S, G = self.orc.preprocess(src, self.v), self.orc.preprocess(tgt, self.v)
+        ro = self.orc.global_registration(S, G, self.v, 2000, 0.999, 7)
+        io = self.orc.refine_registration(S, G, ro.transformation, self.v)
+        self.calls.append(len(src))
+        return SimpleNamespace(icp=SimpleNamespace(transformation=io.transformation.reshape(-1), fitness=io.fitness,
+                                                   inlier_rmse=io.inlier_rmse))
+
+
+def _batch_pairs():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "3d-matching_b200"))
+    from pcr_b200 import synth
+    return [synth.make_pair(1500 + 100 * i, 0.02, 900 + i)[:2] for i in range(5)]
+
+
+def _batch_worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        pairs = _batch_pairs()
+        from oracle import pcr_oracle as orc
+        orc.build()
+        orc.set_num_threads(1)
+        from pcr_b200.dist import align_batch
+        eng = _OracleEngine(orc, 0.02)
+        # a rank only materialises its own pairs (the others are None, as bench.py's batch leg does)
+        mine = [p if i % world == rank else None for i, p in enumerate(pairs)]
+        tab = align_batch(eng, mine, None)
+        q.put((rank, tab.tolist(), eng.calls))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put(("error", repr(e), None))
+        raise
+
+
+def test_align_batch_shards_pairs_and_gathers_on_two_ranks():
+    pairs = _batch_pairs()
+    from oracle import pcr_oracle as orc
+    orc.build()
+    eng = _OracleEngine(orc, 0.02)
+    sys.path.insert(0, os.path.join(ROOT, "3d-matching_b200"))
+    from pcr_b200.dist import align_batch
+    want = align_batch(eng, pairs, None)  # no process group: everything on this process
+    assert want.shape == (5, 18) and (want[:, 16] > 0.5).all()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    assert all(g[0] != "error" for g in got), got
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, tab, calls in got:
+        assert np.array_equal(np.array(tab), want)                      # every rank holds the whole table, pair order kept
+        assert calls == [len(pairs[i][0]) for i in range(rank, 5, 2)]   # and aligned exactly its own pairs, in order
