@@ -332,3 +332,30 @@ def test_ascii_numbers_are_correctly_rounded(tmp_path):
     got = read_ply(p)[0].reshape(-1)
     want = np.array([float(t) for t in toks])
     assert got.tobytes() == want.tobytes(), [(t, g, w) for t, g, w in zip(toks, got, want) if not (g == w and np.signbit(g) == np.signbit(w))][:5]
+
+
+def test_reader_is_reentrant_across_threads(tmp_path):
+    """ctypes releases the GIL: concurrent reads of different files from Python threads (the GUI calls the matcher from
+    worker threads, _visualize_matcher.py:264,275,292) do not interfere."""
+    import threading
+    files = []
+    for i in range(6):
+        p = tmp_path / f"f{i}.ply"
+        pts = cloud(40_000 + 1000 * i, seed=100 + i).astype(np.float32)
+        write_ply(p, pts, binary=bool(i % 2))
+        files.append((p, pts))
+    bad = []
+
+    def work(k):
+        for rep in range(4):
+            p, pts = files[(k + rep) % len(files)]
+            got = read_ply_xyzw(p, pin=False)[0].numpy()[:, :3]
+            if not same(got, pts):
+                bad.append((k, rep))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not bad, bad
