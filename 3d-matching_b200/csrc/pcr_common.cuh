@@ -57,12 +57,27 @@ struct IcpPrep {
     bool valid = false;
 };
 
+// EXPERIMENTAL (off unless PCR_VAL_LISTS=1; pcr_celllists.cu): per-fine-cell candidate lists over the target cloud.
+// For a fine cell C (side c = radius / (1.5 div)) the list holds every target point t with
+// dmin(t, C) <= min(min_t' dmax(t', C), r) (1 + 1e-5): the nearest neighbour of EVERY query inside C is on the list, so a
+// radius-limited 1-NN tests 3-6 points instead of walking 27 coarse cells.  The winner is chosen with the same fp32
+// distance and (d2, index) key as grid_nn1, hence identical results (NumPy prototype + proof:
+// tools/proto/cell_candidate_lists.py).  Not yet measured on the GPU.
+struct CellLists {
+    const uint32_t *head;  // per fine cell: (offset << 4) | count; count 15 = list too long -> full search
+    const float4 *items;   // candidate points, .w = original index (int bits)
+    double ox, oy, oz, inv_c;
+    int nx, ny, nz;
+};
+
 // prepared RANSAC work (target grid + spatially sorted source), see pcr_ransac.cu
 struct RansacWork {
     Grid g;
     const float4 *src_sorted;
     float r2;
     int k_d;
+    CellLists cl;
+    bool use_lists;
 };
 
 struct pcr_ctx {
@@ -186,6 +201,8 @@ int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, 
 // Morton-order copy of a cloud (dense counting sort on interleaved cell ids; .w = original index): consecutive
 // points are spatially compact, which the warp-cooperative joins rely on
 int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out);
+// EXPERIMENTAL candidate lists over the points of a grid (pcr_celllists.cu); *ok = false: keep the full search
+int pcr_celllists_build(pcr_ctx *ctx, const Grid &g, double r, int div, CellLists *out, bool *ok);
 // exclusive scan helpers (in pcr_grid.cu)
 int pcr_exclusive_scan_u32(pcr_ctx *ctx, uint32_t *data, long long n);  // in place, data[n] must exist (total)
 int pcr_exclusive_scan_u64(pcr_ctx *ctx, unsigned long long *data, long long n);
@@ -363,6 +380,32 @@ __device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, 
 
 __device__ __forceinline__ int grid_nn1(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
     return grid_nn1_seeded(g, qx, qy, qz, r2, -1, nullptr, d2_out);
+}
+
+// radius-limited 1-NN through the candidate lists: same result as grid_nn1 (see CellLists)
+__device__ __forceinline__ int lists_nn1(const CellLists &L, const Grid &g, float qx, float qy, float qz, float r2, float *d2_out) {
+    typedef unsigned long long u64k;
+    const double fx = ((double)qx - L.ox) * L.inv_c, fy = ((double)qy - L.oy) * L.inv_c, fz = ((double)qz - L.oz) * L.inv_c;
+    // outside the lattice (it pads the cloud by more than the radius), or NaN: no target point within the radius
+    if (!(fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < (double)L.nx && fy < (double)L.ny && fz < (double)L.nz)) {
+        *d2_out = r2;
+        return -1;
+    }
+    const uint32_t h = __ldg(L.head + ((long long)(int)fz * L.ny + (int)fy) * L.nx + (int)fx);
+    const uint32_t cnt = h & 15u;
+    if (cnt == 15u) return grid_nn1(g, qx, qy, qz, r2, d2_out);
+    const float4 *__restrict__ it = L.items + (h >> 4);
+    const uint32_t r2bits = __float_as_uint(r2);
+    u64k bkey = ((u64k)r2bits) << 32;
+    for (uint32_t k = 0; k < cnt; k++) {
+        const float4 p = __ldg(it + k);
+        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+        const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
+        bkey = key < bkey ? key : bkey;
+    }
+    const uint32_t hi = (uint32_t)(bkey >> 32);
+    *d2_out = __uint_as_float(hi);
+    return hi < r2bits ? (int)(uint32_t)(bkey & 0xffffffffull) : -1;
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {

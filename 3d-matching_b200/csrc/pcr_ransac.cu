@@ -261,13 +261,13 @@ __device__ __forceinline__ void ransac_effective_best(const Survivor *surv, cons
     *os = q;
 }
 
-template <int VAL_THREADS>
+template <int VAL_THREADS, bool LISTS = false>
 __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g, const int2 *__restrict__ corr, int c,
     double max_dist, float r2, double sc_d, Survivor *__restrict__ surv, const unsigned int *__restrict__ n_surv,
     long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs, unsigned int *__restrict__ n_recs,
     unsigned int rec_cap, int chunk_stride, unsigned int *__restrict__ next_surv, int *__restrict__ bucket_best,
-    long long hyp_begin, long long hyp_count) {
+    long long hyp_begin, long long hyp_count, CellLists L) {
     __shared__ double sT[12];
     __shared__ long long red[VAL_THREADS / 32][3];
     __shared__ long long s_best[2];
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
                 const float4 p = __ldg(src + i);
                 const float3 q = xform_pt(T, p.x, p.y, p.z);
                 float d2;
-                if (grid_nn1(g, q.x, q.y, q.z, r2, &d2) >= 0) {
+                if ((LISTS ? lists_nn1(L, g, q.x, q.y, q.z, r2, &d2) : grid_nn1(g, q.x, q.y, q.z, r2, &d2)) >= 0) {
                     hit = true;
                     cnt++;
                     q_add = fixed_ll((double)d2, sc_d);
@@ -465,6 +465,15 @@ int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tg
     PCR_TRY(pcr_morton_sort(ctx, src, ms, &w->src_sorted));
     w->r2 = (float)(max_dist * max_dist);
     w->k_d = pcr_ransac_k_d(max_dist, ms);
+    // EXPERIMENTAL: PCR_VAL_LISTS=1 (c = v/2) or =3 (c = v/3) validates through per-cell candidate lists (pcr_celllists.cu)
+    w->use_lists = false;
+    w->cl = CellLists{};
+    static const int lists_div = getenv("PCR_VAL_LISTS") ? atoi(getenv("PCR_VAL_LISTS")) : 0;
+    if (lists_div > 0) {
+        bool ok = false;
+        PCR_TRY(pcr_celllists_build(ctx, w->g, max_dist, lists_div >= 2 ? lists_div : 2, &w->cl, &ok));
+        w->use_lists = ok;
+    }
     return PCR_OK;
 }
 
@@ -478,6 +487,7 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
     pcr_ransac_session_end_impl(ctx);
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
+    w.use_lists = false;  // the experimental candidate lists live in the per-call arena and are not carried by a session
     const size_t ncells = (size_t)w.g.nx * w.g.ny * w.g.nz;
     const size_t bytes[3] = {sizeof(float4) * (size_t)mt, sizeof(uint32_t) * (ncells + 1), sizeof(float4) * (size_t)ms};
     const void *from[3] = {w.g.sorted, w.g.start, w.src_sorted};
@@ -555,14 +565,18 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     }
     {
         KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
-#define PCR_VAL_LAUNCH(NT)                                                                                                       \
-        k_ransac_validate<NT><<<vblocks, NT, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist, w.r2, \
-                                                               ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, recs,       \
-                                                               counters + 1, (unsigned int)cap, stride, counters + 2, bucket_best,    \
-                                                               hyp_begin, count)
-        if (vthreads == 1024) PCR_VAL_LAUNCH(1024);
-        else if (vthreads == 512) PCR_VAL_LAUNCH(512);
-        else PCR_VAL_LAUNCH(256);
+#define PCR_VAL_LAUNCH(NT, LS)                                                                                                   \
+        k_ransac_validate<NT, LS><<<vblocks, NT, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,  \
+                                                                   w.r2, ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, \
+                                                                   recs, counters + 1, (unsigned int)cap, stride, counters + 2,   \
+                                                                   bucket_best, hyp_begin, count, w.cl)
+        if (w.use_lists) {  // EXPERIMENTAL (PCR_VAL_LISTS): same kernel, nearest neighbours through the candidate lists
+            if (vthreads == 1024) PCR_VAL_LAUNCH(1024, true);
+            else if (vthreads == 512) PCR_VAL_LAUNCH(512, true);
+            else PCR_VAL_LAUNCH(256, true);
+        } else if (vthreads == 1024) PCR_VAL_LAUNCH(1024, false);
+        else if (vthreads == 512) PCR_VAL_LAUNCH(512, false);
+        else PCR_VAL_LAUNCH(256, false);
 #undef PCR_VAL_LAUNCH
         PCR_LAUNCHED();
     }
