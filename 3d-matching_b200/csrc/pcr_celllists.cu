@@ -71,6 +71,7 @@ int pcr_celllists_build(pcr_ctx *ctx, const Grid &g, double r, int div, CellList
     out->nx = fnx;
     out->ny = fny;
     out->nz = fnz;
+    out->cap = cap;
     *ok = true;
     return PCR_OK;
 }

@@ -68,6 +68,7 @@ struct CellLists {
     const float4 *items;   // candidate points, .w = original index (int bits)
     double ox, oy, oz, inv_c;
     int nx, ny, nz;
+    unsigned int cap;      // capacity of `items` (host bookkeeping)
 };
 
 // prepared RANSAC work (target grid + spatially sorted source), see pcr_ransac.cu
@@ -114,8 +115,9 @@ struct pcr_ctx {
         int ms = 0, mt = 0;
         double max_dist = 0.0;
         RansacWork w;
-        void *bufs[3] = {nullptr, nullptr, nullptr};  // grid.sorted, grid.start, src_sorted (grow-only, freed at destroy)
-        size_t cap[3] = {0, 0, 0};
+        // grid.sorted, grid.start, src_sorted, and (experimental candidate lists) head, items: grow-only, freed at destroy
+        void *bufs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        size_t cap[5] = {0, 0, 0, 0, 0};
     } rsess;
     // pcr_align overlaps independent stages (the two clouds' preprocessing; full-resolution normals next to RANSAC) on
     // a second context with its own stream, arena and pinned page, driven by one persistent host thread (the stages

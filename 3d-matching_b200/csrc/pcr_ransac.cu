@@ -487,11 +487,13 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
     pcr_ransac_session_end_impl(ctx);
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
-    w.use_lists = false;  // the experimental candidate lists live in the per-call arena and are not carried by a session
     const size_t ncells = (size_t)w.g.nx * w.g.ny * w.g.nz;
-    const size_t bytes[3] = {sizeof(float4) * (size_t)mt, sizeof(uint32_t) * (ncells + 1), sizeof(float4) * (size_t)ms};
-    const void *from[3] = {w.g.sorted, w.g.start, w.src_sorted};
-    for (int i = 0; i < 3; i++) {
+    // the experimental candidate lists (PCR_VAL_LISTS) are carried like the grid: header words + the whole item pool
+    const size_t lcells = w.use_lists ? (size_t)w.cl.nx * w.cl.ny * w.cl.nz : 0;
+    const size_t bytes[5] = {sizeof(float4) * (size_t)mt, sizeof(uint32_t) * (ncells + 1), sizeof(float4) * (size_t)ms,
+                             sizeof(uint32_t) * lcells, w.use_lists ? sizeof(float4) * (size_t)w.cl.cap : 0};
+    const void *from[5] = {w.g.sorted, w.g.start, w.src_sorted, w.cl.head, w.cl.items};
+    for (int i = 0; i < (w.use_lists ? 5 : 3); i++) {
         if (ctx->rsess.cap[i] < bytes[i]) {
             if (ctx->rsess.bufs[i]) PCR_CUDA(cudaFree(ctx->rsess.bufs[i]));
             ctx->rsess.bufs[i] = nullptr;
@@ -505,6 +507,10 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
     w.g.sorted = (const float4 *)ctx->rsess.bufs[0];
     w.g.start = (const uint32_t *)ctx->rsess.bufs[1];
     w.src_sorted = (const float4 *)ctx->rsess.bufs[2];
+    if (w.use_lists) {
+        w.cl.head = (const uint32_t *)ctx->rsess.bufs[3];
+        w.cl.items = (const float4 *)ctx->rsess.bufs[4];
+    }
     ctx->rsess.w = w;
     ctx->rsess.src = src; ctx->rsess.tgt = tgt; ctx->rsess.ms = ms; ctx->rsess.mt = mt; ctx->rsess.max_dist = max_dist;
     ctx->rsess.active = true;
