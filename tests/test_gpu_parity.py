@@ -399,3 +399,20 @@ def test_align_degenerate_inputs_follow_the_oracle(orc, eng, case):
     assert np.array_equal(np.array(info.ransac.transformation).reshape(4, 4), ro.transformation), name
     assert np.array_equal(T, io.transformation) and fit == io.fitness and rmse == io.inlier_rmse, name
     assert info.icp.iterations == io.iterations, name
+
+
+def test_pipeline_matches_the_committed_golden(eng):
+    """The CUDA path against a COMMITTED fixture (tests/golden/pipeline_golden.npz: the oracle's outputs for the pair that
+    __graft_entry__.smoke() aligns), not only against a live oracle run."""
+    import os
+    from pcr_b200 import align
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_golden.npz"))
+    v = 0.005
+    src, tgt, T_true = synth.make_pair(8000, v, 123)
+    assert np.array_equal(T_true, g["T_true"])
+    T, fit, rmse, info = align(src, tgt, v, ransac_iteration=20000, seed=5, return_info=True)
+    assert np.array_equal(T, g["icp_T"]) and fit == float(g["icp_fitness"]) and rmse == float(g["icp_inlier_rmse"])
+    assert info.ransac.best_hyp == int(g["ransac_best_hyp"]) and info.icp.inlier_count == int(g["icp_inlier_count"])
+    assert np.array_equal(np.array(info.ransac.transformation).reshape(4, 4), g["ransac_T"])
+    assert (info.n_src_down, info.n_tgt_down, info.n_corr) == (len(g["src_down"]), len(g["tgt_down"]), len(g["corr"]))
+    assert info.icp.iterations == int(g["icp_iterations"])
