@@ -36,26 +36,28 @@ int pcr_ransac_step_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, con
 int pcr_inlier_count_impl(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, const double *T,
                           int count, double thresh, int squared, int *counts);
 
+int pcr_corr_check_impl(pcr_ctx *ctx, const int *corr, int c, int ms, int mt);
 int pcr_pack_impl(pcr_ctx *ctx, const float *xyz, int n, float4 *out);
 
 struct CallGuard {
     pcr_ctx *ctx;
     bool ok;
     explicit CallGuard(pcr_ctx *c) : ctx(c), ok(false) {
-        if (!ctx || ctx->busy) return;
-        ctx->busy = true;
+        if (!ctx) return;
+        bool expected = false;
+        if (!ctx->busy.compare_exchange_strong(expected, true, std::memory_order_acquire)) return;
         ok = true;
         cudaSetDevice(ctx->device);
         pcr_arena_reset(ctx);
     }
     ~CallGuard() {
-        if (ok) ctx->busy = false;
+        if (ok) ctx->busy.store(false, std::memory_order_release);
     }
 };
 #define PCR_ENTER()                   \
     if (!ctx) return PCR_ERR_INVALID; \
     CallGuard guard__(ctx);           \
-    if (!guard__.ok) return pcr_fail(ctx, PCR_ERR_BUSY, "context is in use by another call")
+    if (!guard__.ok) return PCR_ERR_BUSY /* the message buffer belongs to the call in progress: not touched */
 #define PCR_ARG(cond) \
     if (!(cond)) return pcr_fail(ctx, PCR_ERR_INVALID, "invalid argument: %s", #cond)
 
@@ -111,6 +113,7 @@ int pcr_ransac(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt,
                pcr_reg_result *result) {
     PCR_ENTER();
     PCR_ARG(ms >= 0 && mt >= 0 && c >= 0 && result);
+    PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
     return pcr_ransac_impl(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, corr, c, max_dist, edge_sim, max_iter,
                            confidence, seed, result);
 }
@@ -122,11 +125,18 @@ int pcr_ransac_wave(pcr_ctx *ctx, const float *src, int ms, const float *tgt, in
     PCR_ENTER();
     PCR_ARG(ms > 0 && mt > 0 && c >= 3 && max_dist > 0.0 && records && cap > 0 && n_records && n_survivors);
     RansacWork w;
-    const auto &rs = ctx->rsess;
-    if (rs.active && rs.src == (const void *)src && rs.tgt == (const void *)tgt && rs.ms == ms && rs.mt == mt && rs.max_dist == max_dist)
+    auto &rs = ctx->rsess;
+    if (rs.active && rs.src == (const void *)src && rs.tgt == (const void *)tgt && rs.ms == ms && rs.mt == mt && rs.max_dist == max_dist) {
         w = rs.w;  // inside a session on these clouds: the grid and the sorted source are already there
-    else
+        if (rs.corr_ok != (const void *)corr || rs.corr_ok_c != c) {  // validated once per session and buffer
+            PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
+            rs.corr_ok = corr;
+            rs.corr_ok_c = c;
+        }
+    } else {
+        PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
         PCR_TRY(pcr_ransac_prepare(ctx, (const float4 *)src, ms, (const float4 *)tgt, mt, max_dist, &w));
+    }
     long long ns = 0;
     const int rc = pcr_ransac_wave_impl(ctx, w, (const float4 *)src, ms, (const float4 *)tgt, corr, c, max_dist, edge_sim,
                                         hyp_begin, hyp_end, seed, best_count, best_sum, records, cap, n_records, &ns);
@@ -145,17 +155,19 @@ int pcr_ransac_session_end(pcr_ctx *ctx) {
     return pcr_ransac_session_end_impl(ctx);
 }
 
-int pcr_ransac_step(pcr_ctx *ctx, const float *src, const float *tgt, const int *corr, int c, uint64_t seed,
+int pcr_ransac_step(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt, const int *corr, int c, uint64_t seed,
                     int64_t h_begin, int count, double *T) {
     PCR_ENTER();
-    PCR_ARG(c >= 0 && count >= 0);
+    PCR_ARG(ms >= 0 && mt >= 0 && c >= 0 && count >= 0);
+    PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
     return pcr_ransac_step_impl(ctx, (const float4 *)src, (const float4 *)tgt, corr, c, seed, h_begin, count, T);
 }
 
-int pcr_inlier_count(pcr_ctx *ctx, const float *src, const float *tgt, const int *corr, int c, const double *T,
+int pcr_inlier_count(pcr_ctx *ctx, const float *src, int ms, const float *tgt, int mt, const int *corr, int c, const double *T,
                      int count, double thresh, int squared, int *counts) {
     PCR_ENTER();
-    PCR_ARG(c >= 0 && count >= 0);
+    PCR_ARG(ms >= 0 && mt >= 0 && c >= 0 && count >= 0);
+    PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
     return pcr_inlier_count_impl(ctx, (const float4 *)src, (const float4 *)tgt, corr, c, T, count, thresh, squared,
                                  counts);
 }

@@ -104,7 +104,11 @@ struct pcr_ctx {
     // pinned staging for file input (pcr_align_files): grow-only, freed at destroy
     void *stage = nullptr;
     size_t stage_bytes = 0;
-    bool busy = false;
+    std::atomic<bool> busy{false};  // one exported call at a time per context: the second caller gets PCR_ERR_BUSY
+    // per-context (hence per-device and per-owner-thread) launch-configuration caches: occupancy and function
+    // attributes are properties of (function, device), and contexts may be created from several host threads
+    int occ_icp = 0, occ_val256 = 0, occ_val512 = 0;
+    bool match_tc_attr_set = false;
     // bounding boxes already reduced during the current exported call, keyed by (pointer, n); cleared on entry
     struct BoundsEntry { const void *ptr; int n; float lo[3], hi[3]; };
     std::vector<BoundsEntry> bounds_cache;
@@ -114,6 +118,8 @@ struct pcr_ctx {
         const void *src = nullptr, *tgt = nullptr;
         int ms = 0, mt = 0;
         double max_dist = 0.0;
+        const void *corr_ok = nullptr;  // correspondence buffer already validated against (ms, mt) in this session
+        int corr_ok_c = 0;
         RansacWork w;
         // grid.sorted, grid.start, src_sorted, and (experimental candidate lists) head, items: grow-only, freed at destroy
         void *bufs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

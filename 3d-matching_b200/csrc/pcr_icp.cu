@@ -586,7 +586,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     float r2 = (float)(max_dist * max_dist);
     // cooperative launch: every CTA must be resident (the kernel synchronises the grid once per pass)
-    static int occ = 0;
+    int &occ = ctx->occ_icp;
     if (!occ) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp_persist, ICP_THREADS, 0));
     if (occ < 1) return pcr_fail(ctx, PCR_ERR_CUDA, "k_icp_persist does not fit on an SM");
     const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * occ);

@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(256) k_corr_compact(const int *__restrict__ nn
     }
 }
 
-__global__ void __launch_bounds__(256) k_corr_all(const int *__restrict__ nn_s, int ms, int *__restrict__ corr) {
+// one-directional set: every source descriptor with a nearest target descriptor (a descriptor holding a NaN has none,
+// nn = -1, and contributes no pair — an index of -1 would be an out-of-bounds read in every consumer)
+__global__ void __launch_bounds__(256) k_valid_flags(const int *__restrict__ nn_s, int ms, uint32_t *__restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ms) return;
-    corr[2 * (size_t)i] = i;
-    corr[2 * (size_t)i + 1] = nn_s[i];
+    flags[i] = nn_s[i] >= 0 ? 1u : 0u;
 }
 
 int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn);
@@ -98,28 +99,33 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
     if (ms == 0 || mt == 0) return PCR_OK;
     PCR_ALLOC(nn_s, int, (size_t)ms);
     PCR_TRY(pcr_nn_features_impl(ctx, fs, ms, ft, mt, nn_s));
+    PCR_ALLOC(pos, uint32_t, (size_t)ms + 1);
+    uint32_t *h = (uint32_t *)ctx->pinned;
     if (mutual) {
         PCR_ALLOC(nn_t, int, (size_t)mt);
-        PCR_ALLOC(pos, uint32_t, (size_t)ms + 1);
         PCR_TRY(pcr_nn_features_impl(ctx, ft, mt, fs, ms, nn_t));
         k_mutual_flags<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, nn_t, ms, pos);
         PCR_LAUNCHED();
         PCR_TRY(pcr_exclusive_scan_u32(ctx, pos, ms));
         k_corr_compact<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, pos, ms, corr);
         PCR_LAUNCHED();
-        uint32_t *h = (uint32_t *)ctx->pinned;
         PCR_CUDA(cudaMemcpyAsync(h, pos + ms, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         PCR_CUDA(cudaStreamSynchronize(ctx->stream));
         const int c = (int)*h;
-        if ((double)c >= mutual_ratio * (double)ms) {
+        // Open3D: int(corres_mutual.size()) >= int(mutual_consistency_ratio * num_src) — both sides truncated (A.5)
+        if (c >= (int)(mutual_ratio * (double)ms)) {
             *c_host = c;
             return PCR_OK;
         }
         // too few mutual pairs: fall back to the one-directional set (A.5)
     }
-    k_corr_all<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, ms, corr);
+    k_valid_flags<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, ms, pos);
     PCR_LAUNCHED();
-    PCR_CUDA(cudaGetLastError());
-    *c_host = ms;
+    PCR_TRY(pcr_exclusive_scan_u32(ctx, pos, ms));
+    k_corr_compact<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, pos, ms, corr);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaMemcpyAsync(h, pos + ms, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *c_host = (int)*h;
     return PCR_OK;
 }

@@ -534,10 +534,9 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
     PCR_ALLOC(n_fb, unsigned int, 4);
     PCR_CUDA(cudaMemsetAsync(n_fb, 0, 16, ctx->stream));
     const size_t smem = (size_t)TC_A_BYTES + 2 * (size_t)TC_B_BYTES + sizeof(TcSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->match_tc_attr_set) {  // per device: set once per context
         PCR_CUDA(cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->match_tc_attr_set = true;
     }
     const int items = A.n_tiles * n_split;
     {

@@ -7,8 +7,6 @@ import torch
 from pcr_b200.containers import Feature, PointCloud
 from pcr_b200.engine import get_engine
 
-_cache: dict = {}
-
 
 def device_cloud(pcd, eng=None) -> torch.Tensor:
     """Packed float4 device tensor of a PointCloud or of any object with an array-like `.points`
@@ -22,15 +20,9 @@ def device_cloud(pcd, eng=None) -> torch.Tensor:
     arr = np.asarray(pts)
     if arr.size == 0:
         return torch.zeros((0, 4), dtype=torch.float32, device=eng.tdev)
-    key = (id(pts), arr.shape, arr.__array_interface__["data"][0])
-    hit = _cache.get(key)
-    if hit is not None and hit[0] is pts:
-        return hit[1]
-    t = eng.pack(arr)
-    if len(_cache) > 16:
-        _cache.clear()
-    _cache[key] = (pts, t)  # holding `pts` keeps id() unique for the lifetime of the entry
-    return t
+    # No cache: the reference re-reads np.asarray(pcd.points) on every call (src/matcher/ransac.py:147-148, :223-224), and
+    # callers do change clouds in place between calls (pcd.transform, `pts += ...`); a 10k-point pack is ~20 us.
+    return eng.pack(arr)
 
 
 def device_feature(f, eng=None) -> torch.Tensor:
@@ -49,6 +41,19 @@ def device_corr(corr, eng=None) -> torch.Tensor:
         return corr.to(eng.tdev, torch.int32).reshape(-1, 2).contiguous()
     a = np.ascontiguousarray(np.asarray(corr, dtype=np.int32).reshape(-1, 2))
     return torch.from_numpy(a).to(eng.tdev)
+
+
+class index_errors:
+    """The reference raises IndexError for a correspondence that points outside a cloud (NumPy fancy indexing,
+    src/matcher/ransac.py:147-148, :223-224); the C ABI reports it as PCR_ERR_INVALID -> ValueError."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is ValueError and "indexes outside the clouds" in str(ev):
+            raise IndexError(str(ev)) from None
+        return False
 
 
 def voxel_of(obj, voxel_size):

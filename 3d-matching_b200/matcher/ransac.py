@@ -23,7 +23,7 @@ import torch
 from pcr_b200.containers import RegistrationResult
 from pcr_b200.engine import get_engine
 
-from ._common import device_cloud, device_corr, device_feature, voxel_of
+from ._common import device_cloud, device_corr, device_feature, index_errors, voxel_of
 
 _step_counter = itertools.count()
 
@@ -80,7 +80,8 @@ def compute_step_transformation(src, tgt, correspondences, *, seed: int = 0, ind
         return res
     eng = get_engine()
     h = next(_step_counter) if index is None else int(index)
-    T = eng.ransac_step(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng), seed, h, 1)
+    with index_errors():
+        T = eng.ransac_step(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng), seed, h, 1)
     res.transformation = T[0].cpu().numpy()
     return res
 
@@ -88,8 +89,9 @@ def compute_step_transformation(src, tgt, correspondences, *, seed: int = 0, ind
 def compute_step_transformations(src, tgt, correspondences, count: int, *, seed: int = 0, start: int = 0) -> torch.Tensor:
     """Batched twin: `count` hypotheses in one launch; returns a (count,4,4) fp64 CUDA tensor."""
     eng = get_engine()
-    return eng.ransac_step(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng),
-                           device_corr(correspondences, eng), seed, start, count)
+    with index_errors():
+        return eng.ransac_step(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng),
+                               device_corr(correspondences, eng), seed, start, count)
 
 
 def evaluate_inlier_ratio(src, tgt, correspondences, transform, voxel_size: float) -> float:
@@ -99,8 +101,9 @@ def evaluate_inlier_ratio(src, tgt, correspondences, transform, voxel_size: floa
         return 0.0
     eng = get_engine()
     T = torch.as_tensor(np.asarray(transform, np.float64).reshape(1, 4, 4))
-    cnt = eng.inlier_count(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng), T,
-                           dist_thresh, squared=False)
+    with index_errors():
+        cnt = eng.inlier_count(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng), T,
+                               dist_thresh, squared=False)
     return float(cnt[0].item()) / len(corr)
 
 
@@ -110,8 +113,9 @@ def evaluate_inlier_ratios(src, tgt, correspondences, transforms, voxel_size: fl
     if len(corr) == 0:
         return np.zeros(len(transforms))
     eng = get_engine()
-    cnt = eng.inlier_count(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng),
-                           torch.as_tensor(transforms), voxel_size * 1.5, squared=False)
+    with index_errors():
+        cnt = eng.inlier_count(device_cloud(src.pcd_down, eng), device_cloud(tgt.pcd_down, eng), device_corr(corr, eng),
+                               torch.as_tensor(transforms), voxel_size * 1.5, squared=False)
     return cnt.cpu().numpy() / float(len(corr))
 
 
@@ -166,8 +170,9 @@ def run_ransac_manual(src, tgt, voxel_size: float | None = None, max_iter: int =
     best_fitness, have_best, it = -1.0, False, 0
     while it < max_iter:
         n = min(batch, max_iter - it)
-        Ts = eng.ransac_step(s, t, c, seed, it, n)
-        w = (eng.inlier_count(s, t, c, Ts, thresh_sq, squared=True).cpu().numpy() / float(len(corres)))
+        with index_errors():
+            Ts = eng.ransac_step(s, t, c, seed, it, n)
+            w = (eng.inlier_count(s, t, c, Ts, thresh_sq, squared=True).cpu().numpy() / float(len(corres)))
         Ts_h = None
         for k in range(n):
             if should_stop is not None and should_stop():

@@ -138,6 +138,8 @@ def check(lib, ctx, rc: int) -> None:
     """Map pcr_status onto the exceptions the reference raises (src/ply/ply.py:46-51,81-84; Open3D RuntimeError)."""
     if rc == PCR_OK:
         return
+    if rc == PCR_ERR_BUSY:  # the message buffer belongs to the call in progress on that context
+        raise PcrError("libpcr_b200: context is in use by another call (PCR_ERR_BUSY)")
     msg = lib.pcr_last_error(ctx)
     msg = msg.decode() if msg else ""
     if rc in (PCR_ERR_INVALID, PCR_ERR_TOO_LARGE):

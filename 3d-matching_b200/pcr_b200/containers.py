@@ -18,7 +18,7 @@ class PointCloud:
     def __init__(self, xyzw: torch.Tensor, normals_xyzw: torch.Tensor | None = None, normals_fn=None):
         self._xyzw = xyzw
         self._normals = normals_xyzw
-        self._normals_fn = normals_fn  # lazy estimator: () -> (n,4) tensor
+        self._normals_fn = normals_fn  # lazy estimator: (xyzw of the cloud at evaluation time) -> (n,4) tensor
         self._points_np = None
 
     # ---- device side --------------------------------------------------------------------------------
@@ -28,9 +28,14 @@ class PointCloud:
 
     @property
     def normals_xyzw(self) -> torch.Tensor | None:
-        if self._normals is None and self._normals_fn is not None:
-            self._normals = self._normals_fn()
+        self._materialise_normals()
         return self._normals
+
+    def _materialise_normals(self) -> None:
+        """Run the lazy estimator (on the CURRENT points: it receives the live tensor) exactly once."""
+        if self._normals is None and self._normals_fn is not None:
+            fn, self._normals_fn = self._normals_fn, None
+            self._normals = fn(self._xyzw)
 
     # ---- Open3D-like host side ------------------------------------------------------------------------
     @property
@@ -45,6 +50,9 @@ class PointCloud:
         a = np.ascontiguousarray(np.asarray(value, dtype=np.float64))
         if a.ndim != 2 or a.shape[1] != 3:
             raise ValueError("points must be (n,3)")
+        # The reference estimates normals EAGERLY (src/ply/ply.py:65, :110) and Open3D keeps them when the points are
+        # replaced: a lazy estimate must therefore be taken on the cloud as it was, before the points change.
+        self._materialise_normals()
         dev = self._xyzw.device
         t = torch.zeros((a.shape[0], 4), dtype=torch.float32, device=dev)
         t[:, :3] = torch.from_numpy(a).to(dev).to(torch.float32)  # quantise to fp32 (rule D1)
@@ -68,6 +76,7 @@ class PointCloud:
     def transform(self, T) -> "PointCloud":
         """In-place rigid transform (points and normals), like open3d's pcd.transform."""
         from .engine import get_engine
+        self._materialise_normals()  # Open3D's transform rotates the (eagerly estimated) normals with the points
         self._xyzw = get_engine(self._xyzw.device.index).transform_points(self._xyzw.contiguous(), T)
         T = torch.as_tensor(np.asarray(T, np.float64), device=self._xyzw.device)
         self._points_np = None

@@ -286,7 +286,8 @@ class Engine:
         T = torch.empty((count, 4, 4), dtype=torch.float64, device=self.tdev)
         with self._lock:
             self._bind_stream()
-            self._check(self.lib.pcr_ransac_step(self.ctx, _ptr(src), _ptr(tgt), _ptr(corr), C.c_int(corr.shape[0]),
+            self._check(self.lib.pcr_ransac_step(self.ctx, _ptr(src), C.c_int(src.shape[0]), _ptr(tgt), C.c_int(tgt.shape[0]),
+                                                 _ptr(corr), C.c_int(corr.shape[0]),
                                                  C.c_uint64(seed), C.c_int64(h_begin), C.c_int(count), _ptr(T)))
         return T
 
@@ -298,7 +299,8 @@ class Engine:
         out = torch.empty((T.shape[0],), dtype=torch.int32, device=self.tdev)
         with self._lock:
             self._bind_stream()
-            self._check(self.lib.pcr_inlier_count(self.ctx, _ptr(src), _ptr(tgt), _ptr(corr), C.c_int(corr.shape[0]),
+            self._check(self.lib.pcr_inlier_count(self.ctx, _ptr(src), C.c_int(src.shape[0]), _ptr(tgt), C.c_int(tgt.shape[0]),
+                                                  _ptr(corr), C.c_int(corr.shape[0]),
                                                   _ptr(T), C.c_int(T.shape[0]), C.c_double(thresh),
                                                   C.c_int(int(squared)), _ptr(out)))
         return out

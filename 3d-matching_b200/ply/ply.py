@@ -45,7 +45,7 @@ class Ply:
         xyzw = eng.pack(pts)
         v = float(voxel_size)
         # full-resolution normals are only needed by point-to-plane ICP on the target: computed on first access
-        self.pcd = PointCloud(xyzw, normals_fn=lambda: eng.estimate_normals(xyzw, 2.0 * v, 30))
+        self.pcd = PointCloud(xyzw, normals_fn=lambda cur: eng.estimate_normals(cur.contiguous(), 2.0 * v, 30))
         self.pcd_down, self.pcd_fpfh = self._preprocess(self.pcd, v)
         if noise_sigma and noise_sigma > 0.0:
             rng = np.random.default_rng(seed)

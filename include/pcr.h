@@ -167,14 +167,18 @@ PCR_API int pcr_ransac_scan(const pcr_hyp_record *records_host, int n, int64_t h
 PCR_API int pcr_ransac_k_d(double max_dist, int ms);
 
 /* ---- manual-step twins (src/matcher/ransac.py:104-277) -------------------------------------------------- */
+/* Every function that takes correspondences (pcr_ransac, pcr_ransac_wave, and the two below) first checks on the
+ * device that each pair indexes inside [0, ms) x [0, mt) and returns PCR_ERR_INVALID otherwise (the reference raises
+ * IndexError for such a pair); inside a pcr_ransac_session a buffer is checked once. */
 /* compute_step_transformation for hypotheses [h_begin, h_begin + count): 3 distinct correspondences drawn by
  * Philox(seed, h), Kabsch.  T_dev: count x 16 fp64. */
-PCR_API int pcr_ransac_step(pcr_ctx *ctx, const float *src_xyzw_dev, const float *tgt_xyzw_dev, const int *corr_dev,
-                            int c, uint64_t seed, int64_t h_begin, int count, double *T_dev);
+PCR_API int pcr_ransac_step(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                            const int *corr_dev, int c, uint64_t seed, int64_t h_begin, int count, double *T_dev);
 /* evaluate_inlier_ratio / _fast for `count` transforms over c correspondences.  squared != 0: test
  * d^2 < thresh (the _fast variant), else ||.|| < thresh.  counts_dev: count int32 inlier counts. */
-PCR_API int pcr_inlier_count(pcr_ctx *ctx, const float *src_xyzw_dev, const float *tgt_xyzw_dev, const int *corr_dev,
-                             int c, const double *T_dev, int count, double thresh, int squared, int *counts_dev);
+PCR_API int pcr_inlier_count(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                             const int *corr_dev, int c, const double *T_dev, int count, double thresh, int squared,
+                             int *counts_dev);
 
 /* ---- ICP (registration_icp + TransformationEstimationPointToPlane, src/matcher/icp.py:42-48) ------------- */
 /* corr_dev: optional (ns) int32, target index per source point or -1. */

@@ -666,13 +666,15 @@ ORC_API int orc_match_features(const float *fs, int ms, const float *ft, int mt,
         orc_nn_features(ft, mt, fs, ms, nn_t);
         for (int i = 0; i < ms; i++) {
             const int j = nn_s[i];
-            if (nn_t[j] == i) { corr[2 * c] = i; corr[2 * c + 1] = j; c++; }
+            if (j >= 0 && nn_t[j] == i) { corr[2 * c] = i; corr[2 * c + 1] = j; c++; }
         }
         free(nn_t);
-        if ((double)c >= mutual_ratio * (double)ms) { free(nn_s); *c_out = c; return 0; }
+        /* Open3D: int(corres_mutual.size()) >= int(mutual_consistency_ratio * num_src) — both sides truncated */
+        if (c >= (int)(mutual_ratio * (double)ms)) { free(nn_s); *c_out = c; return 0; }
         c = 0;
     }
-    for (int i = 0; i < ms; i++) { corr[2 * c] = i; corr[2 * c + 1] = nn_s[i]; c++; }
+    for (int i = 0; i < ms; i++) /* a descriptor holding a NaN has no nearest neighbour (nn = -1): no pair */
+        if (nn_s[i] >= 0) { corr[2 * c] = i; corr[2 * c + 1] = nn_s[i]; c++; }
     free(nn_s);
     *c_out = c;
     return 0;

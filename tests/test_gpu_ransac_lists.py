@@ -1,15 +1,13 @@
-"""EXPERIMENTAL paths that have not run on a GPU yet.  Skipped unless PCR_RUN_EXPERIMENTAL=1, so that the round-end
-`pytest -m gpu` only exercises measured code; run explicitly (first thing next round) with
-    PCR_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
-"""
+"""RANSAC validation through the per-fine-cell candidate lists (pcr_celllists.cu; the default since round 2) and through
+the 27-cell grid walk it replaced (PCR_VAL_LISTS=0, still the fallback for over-long lists and oversized lattices):
+both must reproduce the oracle bit for bit.  The switch is read once per process, hence the subprocesses."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PCR_RUN_EXPERIMENTAL") != "1", reason="set PCR_RUN_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -45,7 +43,7 @@ print("lists ok")
 
 @pytest.mark.parametrize("div", ["0", "1", "3"])
 def test_ransac_through_candidate_lists_equals_the_oracle(div):
-    """PCR_VAL_LISTS is read once per process, hence the subprocess; div 0 = the default path, for the timing next to it."""
+    """div 0 = the grid walk, 1 = lists with cells of v/2 (the default), 3 = cells of v/3."""
     env = dict(os.environ, PCR_VAL_LISTS=div)
     code = _SCRIPT.format(root=ROOT, pkg=os.path.join(ROOT, "3d-matching_b200"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=180)
