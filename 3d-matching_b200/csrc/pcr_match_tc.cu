@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(FB_THREADS) k_match_fallback(const float *__re
                         const int jj = v[p2].j;
                         if (d2 < bd || (d2 == bd && jj < bj)) { bd = d2; bj = jj; }
                     }
-                    nn[rows[r]] = bj;
+                    nn[rows[r]] = bj == 0x7fffffff ? -1 : bj;  // no finite distance (NaN descriptor): no neighbour, as the exact kernel
                 }
             }
         }

@@ -270,15 +270,7 @@ def run_engine(args):
     if dom:
         name, st = dom
         per_launch_ms = st["ms"] / max(st["launches"], 1)
-        if name == "nn_features" and st["flops"] > 0:
-            ach = st["flops"] / (st["ms"] * 1e-3) / 1e12
-            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
-        else:
-            ach = st["bytes"] / (st["ms"] * 1e-3) / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None}
-        roof["traffic"], roof["traffic_source"] = ncu_traffic(name)
+        roof = roofline_of(name, st, peaks, clk)
         roof.update({"avg_launch_us": per_launch_ms * 1e3, "launches_per_step": st["launches"] / args.steps,
                      "share_of_step": st["ms"] / step_total, "peak_source": peaks["source"],
                      "algorithmic_bytes_per_launch": st["bytes"] / max(st["launches"], 1)})
@@ -320,6 +312,11 @@ def run_engine(args):
            "icp_pass_roofline_100k": icp_roof}
     if not args.no_aux:
         aux.update(run_aux(eng, args, world, rank, peaks))
+    if rank == 0 and not args.no_cpu and not args.no_cfg1:
+        try:
+            aux["cfg1"] = run_cfg1(eng, args)
+        except Exception as e:  # an auxiliary leg never takes the headline line down
+            aux["cfg1"] = {"error": f"{type(e).__name__}: {e}"}
 
     if world > 1:
         dist.barrier()
@@ -338,6 +335,13 @@ def run_engine(args):
             "e2e": {"value": ms_e2e / world, "unit": "ms", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(src.nbytes + tgt.nbytes), "d2h_bytes_per_step": int(ctypes_sizeof_result())},
             "gpu_launches": int(launches),
+            # the paths that actually shard, whole job over all ranks, next to the replica headline
+            "ransac_hyp_per_s": (aux.get("ransac") or {}).get("hyp_per_s"),
+            "ransac_identical_to_oracle_golden_10m": (aux.get("ransac") or {}).get("identical_to_oracle_golden_10m"),
+            "batch_pairs_per_s": (aux.get("batch") or {}).get("pairs_per_s_workers3"),
+            "batch_identical_to_oracle": (aux.get("batch") or {}).get("identical_to_oracle"),
+            "icp_iters_per_s_1m": (aux.get("icp_1m") or {}).get("iters_per_s_whole_job"),
+            "icp_1m_identical_to_oracle": (aux.get("icp_1m") or {}).get("identical_to_oracle_10_iterations"),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "result": {"fitness": icp_r.fitness, "inlier_rmse": icp_r.inlier_rmse, "icp_iterations": icp_r.iterations,
                        "ransac_hyp_evaluated": res_e.ransac.hyp_evaluated, "ransac_survivors": res_e.ransac.survivors,
@@ -349,17 +353,186 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
+ISSUE_BOUND = ("ransac_validate", "ransac_generate", "knn_cov", "knn_list")  # working set in L1/L2, DRAM traffic ~ 0
+
+
+def roofline_of(name, st, peaks, clk):
+    """Roofline of one kernel class against the bound that actually binds it: tensor pipe for the
+    descriptor GEMM, thread-instruction issue rate for the L2-resident search kernels (148 SMs x 128 lanes x f_SM;
+    executed thread instructions per launch from the committed ncu capture of the same command), HBM otherwise."""
+    secs = st["ms"] * 1e-3
+    if name == "nn_features" and st["flops"] > 0:
+        ach = st["flops"] / secs / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"]}
+    elif name in ISSUE_BOUND and ncu_field(name, "thread_inst_per_launch"):
+        f_mhz = (clk or {}).get("sm_mhz") or 1965.0
+        peak = 148 * 128 * f_mhz * 1e6 / 1e9  # G thread-instructions / s
+        ach = ncu_field(name, "thread_inst_per_launch") * st["launches"] / secs / 1e9
+        roof = {"kernel": name, "bound": "issue", "achieved": ach, "peak": peak, "unit": "Gthread-inst/s", "frac": ach / peak,
+                "l2_level_algorithmic_gbs": st["bytes"] / secs / 1e9,
+                "note": "thread instructions per launch: smsp__thread_inst_executed.sum of the committed ncu capture; time: live CUDA events"}
+    else:
+        ach = st["bytes"] / secs / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(name)
+    return roof
+
+
+def run_cfg1(eng, args):
+    """BASELINE.json configs[0] / SURVEY 8d cfg 1: the reference's benchmark_ransac.py phases (benchmark_ransac.py:31-220,
+    layout of benchmark_results.txt:6-12) on one synthetic 20k-point pair at the reference's default voxel 0.3
+    (benchmark_ransac.py:46-47 ignores --voxel-size), timed on the host cores beside the GPU:
+      oracle_all / oracle_1core : the CPU oracle (C/OpenMP restatement of the Open3D semantics; open3d is absent);
+      reference_numpy           : the reference's OWN NumPy compute_step_transformation + evaluate_inlier_ratio
+                                  (src/matcher/ransac.py:104-277, unmodified copy in the git-ignored baseline/_ref);
+      gpu                       : this engine through the reference-facing mirror (ply.Ply, matcher.ransac, matcher.icp).
+    Wall clock (perf_counter, device synchronised), best of 3 after one warm-up; ms per call."""
+    import torch
+    from oracle import pcr_oracle as orc
+    from pcr_b200 import synth
+    from matcher.icp import refine_registration
+    from matcher.ransac import (compute_feature_correspondences, compute_step_transformation, compute_step_transformations,
+                                evaluate_inlier_ratio, evaluate_inlier_ratios, global_registration)
+    from ply import Ply
+    orc.build()
+    v, n, iters = 0.3, 20000, 100
+    src, tgt, _ = synth.make_pair(n, v, 20241)
+
+    def best_of(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return min(ts), r
+
+    table = {}
+
+    def oracle_phases(threads, tag):
+        orc.set_num_threads(threads)
+        ms, (S, G) = best_of(lambda: (orc.preprocess(src, v), orc.preprocess(tgt, v)))
+        table.setdefault("ply_loading", {})[tag] = ms
+        ms, corr = best_of(lambda: orc.match_features(S.pcd_fpfh, G.pcd_fpfh, False))
+        table.setdefault("correspondence_computation", {})[tag] = ms
+
+        def steps():
+            for h in range(iters):
+                T, _ = orc.ransac_step(S.pcd_down, G.pcd_down, corr, 0, h)
+                orc.inlier_count(S.pcd_down, G.pcd_down, corr, T, 1.5 * v)
+        ms, _ = best_of(steps)
+        table.setdefault("ransac_iteration", {})[tag] = ms / iters
+        ms, r = best_of(lambda: orc.global_registration(S, G, v, 30, 0.999, 0))
+        table.setdefault("full_ransac", {})[tag] = ms
+        ms, _ = best_of(lambda: orc.refine_registration(S, G, r.transformation, v))
+        table.setdefault("icp_refinement", {})[tag] = ms
+        return S, G, corr, r
+
+    cores = host_threads()
+    S, G, ocorr, oran = oracle_phases(cores, "oracle_all_cores_ms")
+    oracle_phases(1, "oracle_1_core_ms")
+    orc.set_num_threads(cores)
+
+    # the reference's own NumPy path on the same clouds and correspondences
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_numpy
+    ref = ref_numpy.load()
+
+    class _Cloud:
+        def __init__(self, pts):
+            self.points = np.asarray(pts, np.float64)
+
+    class _MockPly:  # the reference's duck type, test_ransac_crash.py:92-96
+        def __init__(self, pts):
+            self.pcd = self.pcd_down = _Cloud(pts)
+            self.pcd_fpfh = None
+
+    if ref is not None:
+        ms_, mt_ = _MockPly(S.pcd_down), _MockPly(G.pcd_down)
+        t_k = t_e = 0.0
+        np.random.seed(0)
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            r_ = ref.compute_step_transformation(ms_, mt_, ocorr)
+            t1 = time.perf_counter()
+            ref.evaluate_inlier_ratio(ms_, mt_, ocorr, r_.transformation, v)
+            t_e += time.perf_counter() - t1
+            t_k += t1 - t0
+        table["ransac_iteration"]["reference_numpy_ms"] = (t_k + t_e) * 1e3 / iters
+        table["compute_transformation"] = {"reference_numpy_ms": t_k * 1e3 / iters}
+        table["evaluate_inliers"] = {"reference_numpy_ms": t_e * 1e3 / iters}
+
+    # this engine, same phases through the mirror of the reference's API
+    ms, (ps, pt) = best_of(lambda: (Ply.from_points(src, v, noise_sigma=0.0), Ply.from_points(tgt, v, noise_sigma=0.0)))
+    table["ply_loading"]["gpu_ms"] = ms  # full-resolution normals are lazy in the mirror: forced below, inside ICP
+    ms, corr = best_of(lambda: compute_feature_correspondences(ps, pt, noise_ratio=0.0))
+    table["correspondence_computation"]["gpu_ms"] = ms
+    same_corr = bool(np.array_equal(corr, ocorr))
+
+    def gpu_steps():
+        for h in range(iters):
+            r_ = compute_step_transformation(ps, pt, corr, seed=0, index=h)
+            evaluate_inlier_ratio(ps, pt, corr, r_.transformation, v)
+    ms, _ = best_of(gpu_steps)
+    table["ransac_iteration"]["gpu_one_at_a_time_ms"] = ms / iters
+    nb = 1 << 20
+
+    def gpu_batched():
+        Ts = compute_step_transformations(ps, pt, corr, nb, seed=0, start=0)
+        return evaluate_inlier_ratios(ps, pt, corr, Ts, v)
+    ms, _ = best_of(gpu_batched)
+    hyp_s_gpu = nb / (ms * 1e-3)
+    ms, rg = best_of(lambda: global_registration(ps, pt, v, 30))
+    table["full_ransac"]["gpu_ms"] = ms
+    _ = pt.pcd.normals_xyzw  # estimate_normals on the full-resolution target (part of ply_loading in the reference)
+    ms, ri = best_of(lambda: refine_registration(ps, pt, rg.transformation, v))
+    table["icp_refinement"]["gpu_ms"] = ms
+    oi = orc.refine_registration(S, G, oran.transformation, v)
+    out = {"workload": "cfg1: 20k-point pair, voxel 0.3 (reference default), benchmark_ransac.py phases; ms per call",
+           "host_cores": cores, "phases": table, "n_down": [int(len(S.pcd_down)), int(len(G.pcd_down))], "n_corr": int(len(ocorr)),
+           "gpu_equals_oracle": {"correspondences": same_corr,
+                                 "ransac_T": bool(np.array_equal(rg.transformation, oran.transformation)),
+                                 "icp_T": bool(np.array_equal(ri.transformation, oi.transformation)),
+                                 "icp_fitness": bool(ri.fitness == oi.fitness)},
+           "manual_step_hyp_per_s": {"gpu_batched_pcr_ransac_step_plus_pcr_inlier_count": hyp_s_gpu,
+                                     "gpu_one_at_a_time": 1e3 / table["ransac_iteration"]["gpu_one_at_a_time_ms"],
+                                     "oracle_all_cores": 1e3 / table["ransac_iteration"]["oracle_all_cores_ms"],
+                                     "reference_numpy": (1e3 / table["ransac_iteration"]["reference_numpy_ms"]) if ref is not None else None,
+                                     "reference_published_benchmark_results_txt": 1e3 / 0.76},
+           "reference_published_ms": {"ply_loading": 791.23, "ransac_iteration": 0.76, "evaluate_inliers": 0.50,
+                                      "compute_transformation": 0.24, "full_ransac": 21.12, "correspondence_computation": 8.98,
+                                      "source": "benchmark_results.txt:6-12 (unknown CPU, unknown clouds)"}}
+    return out
+
+
+def ncu_field(kernel_class, field):
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                e = json.load(f)["kernels"].get(kernel_class)
+            if e and e.get(field) is not None:
+                return e[field]
+        except (OSError, ValueError, KeyError):
+            pass
+    return None
+
+
 def ncu_traffic(kernel_class):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed ncu --set full
-    capture (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None when the class was not captured."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        e = t["kernels"].get(kernel_class)
-        return (e["dram_bytes_per_launch"], f"profiles/r1_traffic.json ({t['source']})") if e else (None, None)
-    except (OSError, ValueError, KeyError):
-        return None, None
+    capture (profiles/r2_traffic.json, else r1; written by tools/ncu_traffic.py); None when the class was not captured."""
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                t = json.load(f)
+            e = t["kernels"].get(kernel_class)
+            if e:
+                return e["dram_bytes_per_launch"], f"profiles/{fn} ({t['source']})"
+        except (OSError, ValueError, KeyError):
+            pass
+    return None, None
 
 
 def ctypes_sizeof_result():
@@ -400,6 +573,23 @@ def run_aux(eng, args, world, rank, peaks):
     out["ransac"] = {"hypotheses": H, "ms": ms, "hyp_per_s": H / (ms * 1e-3), "survivors": r.survivors,
                      "checker_pass_rate": r.survivors / H, "best_hyp": r.best_hyp, "inlier_count": r.inlier_count,
                      "waves": st["waves"], "n_gpus": world}
+    # cfg4 parity: the CPU oracle's sequential loop over the same 10M hypotheses, run once offline (368 s on 8 cores) and
+    # committed (tests/golden/cfg4_ransac_10m.json, made by tests/golden/make_cfg4_golden.py); the sharded run must
+    # reproduce it at every GPU count — winner, counts, fixed-point sum, every bit of T, survivors, consumed iterations
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "cfg4_ransac_10m.json")) as f:
+            gold = json.load(f)
+        if gold["hypotheses"] == H and gold["pair_seed"] == SEED_PAIR:
+            import hashlib
+            Tg = np.array([float.fromhex(x) for x in gold["transformation_hex"]]).reshape(4, 4)
+            same = (r.best_hyp == gold["best_hyp"] and r.inlier_count == gold["inlier_count"]
+                    and r.sum_d2_fixed == gold["sum_d2_fixed"] and r.survivors == gold["survivors"]
+                    and r.hyp_evaluated == gold["hyp_evaluated"] and int(corr.shape[0]) == gold["n_corr"]
+                    and hashlib.sha256(corr.cpu().numpy().tobytes()).hexdigest() == gold["corr_sha256"]
+                    and np.array_equal(np.asarray(r.transformation).reshape(4, 4), Tg))
+            out["ransac"]["identical_to_oracle_golden_10m"] = bool(same)
+    except (OSError, ValueError, KeyError) as e:
+        out["ransac"]["identical_to_oracle_golden_10m"] = f"golden unreadable: {e}"
     # batch of independent pairs (config 5 style: 50k-point pairs, full pipeline, reference-default criteria), pair i ->
     # rank i mod world, no communication until the final all-gather of 18 doubles per pair
     from pcr_b200.dist import align_batch
@@ -410,7 +600,7 @@ def run_aux(eng, args, world, rank, peaks):
             if i % world == rank:
                 s_i, t_i, _ = synth.make_pair(50000, v, 30000 + i)
                 pairs.append((eng.pack(s_i), eng.pack(t_i)))
-                if len(host_pairs) < 2:
+                if rank == 0 and len(host_pairs) < args.batch_check and not args.no_cpu:
                     host_pairs[i] = (s_i, t_i)
             else:
                 pairs.append(None)
@@ -477,6 +667,20 @@ def run_aux(eng, args, world, rank, peaks):
         gbs = ks["bytes"] / (ks["ms"] * 1e-3) / 1e9
         icp.update({"pass_kernel_us": us, "pass_kernel_gbs_algorithmic_52B_per_point": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
                     "kernel_iters_per_s_per_gpu": 1e6 / us})
+    # cfg3 parity: the first 10 iterations of the same 1M-point run against the CPU oracle (src/matcher/icp.py:42-48):
+    # every correspondence index, the inlier count, the fixed-point sum of d2, every bit of T
+    if rank == 0 and not args.no_cpu:
+        from oracle import pcr_oracle as orc
+        orc.build()
+        orc.set_num_threads(host_threads())
+        g10, c10 = eng.icp_point_to_plane(d1s, d1t, nrm, 0.4 * v, np.eye(4), 10, 0.0, 0.0, want_corr=True)
+        t0 = time.perf_counter()
+        o10 = orc.icp_point_to_plane(s1, t1, nrm[:, :3].cpu().numpy(), 0.4 * v, np.eye(4), 10, 0.0, 0.0)
+        icp["oracle_10_iterations_s"] = time.perf_counter() - t0
+        icp["identical_to_oracle_10_iterations"] = bool(
+            np.array_equal(c10.cpu().numpy(), o10.correspondence) and g10.inlier_count == o10.inlier_count
+            and g10.sum_d2_fixed == o10.sum_d2_fixed and np.array_equal(np.asarray(g10.transformation).reshape(4, 4), o10.transformation)
+            and g10.iterations == o10.iterations)
     out["icp_1m"] = icp
     # file -> result on the host (the reference's Ply() starts from PLY files, src/ply/ply.py:80):
     # native pcr_ply_read into pinned packed float4, one H2D copy, the whole alignment.  Wall clock, rank 0 only.
@@ -521,7 +725,9 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the RANSAC hyp/s and 1M-point ICP legs")
     ap.add_argument("--ransac-hyps", type=int, default=10000000)
     ap.add_argument("--icp-points", type=int, default=1000000)
-    ap.add_argument("--batch-pairs", type=int, default=8, help="pairs per GPU of the batch leg (0 = skip)")
+    ap.add_argument("--batch-pairs", type=int, default=128, help="pairs per GPU of the batch leg (cfg5: 128 x 8 GPUs = 1024; 0 = skip)")
+    ap.add_argument("--batch-check", type=int, default=16, help="pairs of the batch re-run through the CPU oracle (cfg5: 16)")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the cfg1 leg (20k pair, per-phase CPU table beside the GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
