@@ -364,6 +364,40 @@ def test_tensor_core_matching_is_exact(orc, eng):
         assert np.array_equal(eng.match_features(dfs, dft, True, 0.0).cpu().numpy(), orc.match_features(fs, ft, True, 0.0))
 
 
+def test_tensor_core_threshold_under_attack(orc, eng):
+    """Adversarial inputs for the error bound eps of the tensor-core filter (pcr_match_tc.cu header):
+    large-norm descriptors (the split-bf16 and fp32-accumulation errors scale with ||a|| ||b||) whose true nearest
+    neighbours differ from dozens of decoys only in the last bits, at several magnitudes, plus rows where the decoys
+    outnumber the list capacity (exact fallback).  If eps were too small the true minimiser would miss the candidate
+    list and the result would differ from the exact fp64 arg-min."""
+    rng = np.random.default_rng(5)
+    for scale in (1.0, 200.0, 3.0e4, 1.0e7):
+        nq, nb = 640, 2304
+        ft = (rng.uniform(0.25, 1.0, (nb, 33)) * scale).astype(np.float32)
+        fs = (rng.uniform(0.25, 1.0, (nq, 33)) * scale).astype(np.float32)
+        # rows 0..199: the query equals a base row up to 1-2 ulp in a few coordinates; 8 decoys of that base row differ
+        # from it by 1 ulp in ONE coordinate each (so exact distances differ in their last digits)
+        for i in range(200):
+            j = 10 * i
+            ft[j + 1:j + 9] = ft[j]
+            for d in range(8):
+                ft[j + 1 + d, d] = np.nextafter(ft[j, d], np.float32(np.inf if d % 2 else -np.inf))
+            fs[i] = ft[j]
+            fs[i, 20] = np.nextafter(np.nextafter(fs[i, 20], np.float32(np.inf)), np.float32(np.inf))
+        # rows 200..219: 40 last-bit decoys each — more than the pass-2 list holds -> exact scan
+        for i in range(200, 220):
+            j = 2010 + 13 * (i - 200) // 1
+            if j + 41 > nb:
+                break
+            ft[j:j + 40] = ft[j]
+            for d in range(40):
+                ft[j + d, d % 33] = np.nextafter(ft[j, d % 33], np.float32(np.inf if d % 3 else -np.inf))
+            fs[i] = ft[j + 17]
+        dfs, dft = torch.from_numpy(fs).cuda(), torch.from_numpy(ft).cuda()
+        assert np.array_equal(eng.nn_features(dfs, dft).cpu().numpy(), orc.nn_features(fs, ft)), scale
+        assert np.array_equal(eng.nn_features(dft, dfs).cpu().numpy(), orc.nn_features(ft, fs)), scale
+
+
 def _degenerate_cases():
     rng = np.random.default_rng(0)
     v = 0.005
