@@ -10,6 +10,7 @@
 // appended to a per-warp shared-memory buffer as 64-bit keys (fp32 d2 bits << 32 | index): key order IS the
 // (d2, index) order of determinism rule D2.  A warp-wide bitonic sort of the buffer yields the neighbour
 // list; when the buffer fills it is sorted and truncated to max_nn and the admission threshold tightens.
+#include <cstdio>
 #include <cstdlib>
 
 #include "pcr_common.cuh"
@@ -211,6 +212,198 @@ __device__ __forceinline__ int warp_knn_top32(const Grid &g, float qx, float qy,
     return found < max_nn ? found : max_nn;
 }
 
+// ---- histogram selection for max_nn <= 32 (round 2) -------------------------------------------------------------------
+// On a dense cloud (full-resolution normals: ~760 candidates in the 27 cells of a radius-sized grid, ~280 inside the
+// radius, 30 wanted) the streaming list above costs ~2,350 warp instructions per query, half of them spent looking at
+// candidates and the rest on 32-wide sort + merge steps.  This path
+//   (1) works on a grid of HALF-radius cells (2 rings) and first looks only at the central 3x3x3 block, which contains
+//       every point closer than one cell size h to the query: if max_nn of the keys seen there are closer than
+//       rho = h (1 - 5e-5), the max_nn nearest neighbours are among them and the other 98 cells are never touched
+//       (~150 candidates instead of ~760 on the dense cloud); otherwise the rest of the 5x5x5 block is appended;
+//   (2) fetches all row ranges of a phase in ONE round trip (a lane per row) and walks them as one flat index space,
+//       128 candidates per step with the 4 loads of a lane in flight together — the search is a chain of dependent
+//       loads, and what bounds it is round trips per query;
+//   (3) appends the in-radius keys to shared memory without ordering them, locates with a 256-bin histogram of d2 / r2
+//       the bin B of the max_nn-th smallest key (on a surface the neighbour count grows like d^2: ~1 key per bin), and
+//       sorts the <= 32 keys of bins <= B once across the warp.  The bin index is monotone in d2, so those keys contain the
+//       max_nn smallest; the (d2, index) order of rule D2 is the key order.
+// Exactly the list warp_knn_top32 returns.  Queries this path cannot take (more than KSEL_CAP keys inside the radius, more
+// than 32 keys up to bin B — a plateau of exact ties —, a grid with other ring counts) return false and take it instead.
+constexpr int KSEL_CAP = 512;   // in-radius keys per warp (4 KB)
+constexpr int KSEL_BINS = 256;
+
+// One phase of the candidate stream: lane l owns the range [beg, beg + len) of the cell-sorted cloud (len may be 0); the
+// 32 ranges are walked as one flat index space.  scratch: 64 words of shared memory.  Appends the keys < thr to skeys,
+// counts the keys < thr_in.  Returns false on overflow.
+__device__ __forceinline__ bool knn_stream_ranges(const Grid &g, float qx, float qy, float qz, u64 thr, u64 thr_in, uint32_t beg,
+                                                  uint32_t len, int lane, uint32_t *scratch, u64 *skeys, int &cnt, int &n_in) {
+    const u64 INF = ~0ull;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return true;
+    __syncwarp();
+    scratch[lane] = incl - len;  // exclusive offset of range `lane`
+    scratch[32 + lane] = beg;
+    __syncwarp();
+    int r = 0;  // this lane's current range: its flat index only grows, so the cursor only moves forward
+#pragma unroll 1
+    for (uint32_t base = 0; base < total; base += 128) {
+        float4 p[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t f = base + 32 * i + lane;
+            p[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (f < total) {
+                while (r < 31 && scratch[r + 1] <= f) r++;
+                p[i] = __ldg(g.sorted + scratch[32 + r] + (f - scratch[r]));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (base + 32 * i >= total) break;  // warp-uniform
+            u64 key = INF;
+            if (base + 32 * i + lane < total) {
+                const float d2 = dist2f(qx, qy, qz, p[i].x, p[i].y, p[i].z);
+                key = (((u64)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p[i].w);
+            }
+            const bool pred = key < thr;
+            const unsigned m = __ballot_sync(0xffffffffu, pred);
+            if (cnt + 32 > KSEL_CAP) return false;  // warp-uniform
+            if (pred) skeys[cnt + __popc(m & lt_mask)] = key;
+            cnt += __popc(m);
+            n_in += __popc(__ballot_sync(0xffffffffu, key < thr_in));
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool warp_knn_select32(const Grid &g, float qx, float qy, float qz, float r2, int max_nn, int lane,
+                                                  u64 *skeys, uint32_t *hist, u64 *best_out, int *count_out) {
+    const int R = g.R;
+    if (R < 1 || R > 2) return false;
+    const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
+    const int cx = (int)fmin(fmax(floor(fx), -4.0), (double)g.nx + 3.0);
+    const int cy = (int)fmin(fmax(floor(fy), -4.0), (double)g.ny + 3.0);
+    const int cz = (int)fmin(fmax(floor(fz), -4.0), (double)g.nz + 3.0);
+    const u64 INF = ~0ull;
+    const u64 thr = ((u64)__float_as_uint(r2)) << 32;  // d2 < r2  <=>  key < thr
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // inner bound (2 rings only): a point with fp32 d2 < rho2 = h^2 (1 - 1e-4) is closer than h (1 - 4e-5) to the query and
+    // therefore lies in the central 3x3x3 block (cell coordinates are fp64, exact to ~1e-13 cells)
+    const float rho2 = fminf((float)(g.h * g.h * (1.0 - 1e-4)), r2);
+    const u64 thr_in = R == 2 ? ((u64)__float_as_uint(rho2)) << 32 : thr;
+    // row ranges: lane l < (2R+1)^2 owns row (dy, dz); S0..S3 = start[] at the x cells  cx-R | cx-1 | cx+2 | cx+R+1
+    const int W = 2 * R + 1;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    bool central = false;
+    if (lane < W * W) {
+        const int dy = lane % W - R, dz = lane / W - R;
+        const int y = cy + dy, z = cz + dz;
+        central = dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1;
+        const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);      // whole row, clamped
+        const int xc = max(cx - 1, 0), xd = min(cx + 1, g.nx - 1);      // central cells, clamped
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz && xa <= xb) {
+            const uint32_t *st = g.start + ((long long)z * g.ny + y) * g.nx;
+            s0 = __ldg(st + xa);
+            s3 = __ldg(st + xb + 1);
+            if (xc <= xd) {
+                s1 = __ldg(st + xc);
+                s2 = __ldg(st + xd + 1);
+            } else {
+                s1 = s2 = s0;  // no central cell inside the grid: everything belongs to the outer phase
+            }
+        }
+    }
+    int cnt = 0, n_in = 0;
+    // phase 1: the central block (1 ring: the whole block)
+    if (!knn_stream_ranges(g, qx, qy, qz, thr, thr_in, R == 2 ? s1 : s0, central ? (R == 2 ? s2 - s1 : s3 - s0) : 0u, lane, hist, skeys,
+                           cnt, n_in))
+        return false;
+    if (R == 2 && n_in < max_nn) {
+        // phase 2: the rest of the 5x5x5 block — left and right parts of the central rows, whole outer rows
+        if (!knn_stream_ranges(g, qx, qy, qz, thr, thr, s0, central ? s1 - s0 : s3 - s0, lane, hist, skeys, cnt, n_in)) return false;
+        if (!knn_stream_ranges(g, qx, qy, qz, thr, thr, s2, central ? s3 - s2 : 0u, lane, hist, skeys, cnt, n_in)) return false;
+    }
+    __syncwarp();
+    if (cnt <= 32) {  // sparse neighbourhood: one key per lane, one sort
+        const u64 v = warp_bitonic_sort32(lane < cnt ? skeys[lane] : INF, lane);
+        __syncwarp();
+        *best_out = v;
+        *count_out = cnt < max_nn ? cnt : max_nn;
+        return true;
+    }
+    // cnt > 32 >= max_nn: locate the bin of the max_nn-th smallest key
+    for (int b = lane; b < KSEL_BINS; b += 32) hist[b] = 0u;
+    __syncwarp();
+    const float scale = (float)KSEL_BINS / r2;
+    for (int k = lane; k < cnt; k += 32) {
+        const float d2 = __uint_as_float((uint32_t)(skeys[k] >> 32));
+        atomicAdd(&hist[min(KSEL_BINS - 1, (int)(d2 * scale))], 1u);
+    }
+    __syncwarp();
+    uint32_t h8[8], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        h8[i] = hist[8 * lane + i];
+        mine += h8[i];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - mine;
+    // the lane whose 8 bins contain the max_nn-th key
+    const bool holder = excl < (uint32_t)max_nn && incl >= (uint32_t)max_nn;
+    int B = 0;
+    uint32_t upto = 0;  // keys in bins <= B
+    if (holder) {
+        uint32_t p = excl;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const bool here = p < (uint32_t)max_nn && p + h8[i] >= (uint32_t)max_nn;
+            if (here) {
+                B = 8 * lane + i;
+                upto = p + h8[i];
+            }
+            p += h8[i];
+        }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, holder)) - 1;
+    B = __shfl_sync(0xffffffffu, B, src);
+    upto = __shfl_sync(0xffffffffu, upto, src);
+    if (upto > 32u) return false;  // a plateau of (near-)ties around the max_nn-th key: the streaming list handles it
+    __syncwarp();
+    // gather the keys of bins <= B, one per lane (the histogram words are reused as the staging area)
+    u64 *out = reinterpret_cast<u64 *>(hist);
+    int sel = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int k = base + lane;
+        u64 key = INF;
+        bool pred = false;
+        if (k < cnt) {
+            key = skeys[k];
+            pred = min(KSEL_BINS - 1, (int)(__uint_as_float((uint32_t)(key >> 32)) * scale)) <= B;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pred);
+        if (pred) out[sel + __popc(m & lt_mask)] = key;
+        sel += __popc(m);
+    }
+    __syncwarp();
+    const u64 v = warp_bitonic_sort32(lane < sel ? out[lane] : INF, lane);
+    __syncwarp();
+    *best_out = v;
+    *count_out = max_nn;
+    return true;
+}
+
 // ---- MODE_LIST: neighbour lists to global memory ------------------------------------------------------------
 // self_order: the queries ARE the indexed cloud: take them in cell order (g.sorted, .w = original index) so that
 // consecutive warps probe the same rows of cells
@@ -241,8 +434,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_list(const float4 *__res
 // so the kernel is limited by its 61 registers (8 CTAs / SM) instead of by the 8 KB-per-warp list buffer (6 CTAs / SM).
 template <bool TOP32>
 __global__ void __launch_bounds__(KNN_WARPS * 32, TOP32 ? 8 : 4) k_knn_cov(const float4 *__restrict__ pts, int n, Grid g, float r2,
-                                                                            int max_nn, double *__restrict__ cov_out) {
-    __shared__ u64 sbuf[KNN_WARPS][TOP32 ? 288 : KNN_CAP];
+                                                                            int max_nn, double *__restrict__ cov_out,
+                                                                            unsigned int *__restrict__ stats) {
+    __shared__ u64 sbuf[KNN_WARPS][TOP32 ? KSEL_CAP : KNN_CAP];
+    __shared__ uint32_t shist[TOP32 ? KNN_WARPS : 1][KSEL_BINS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *buf = sbuf[warp];
     // Queries are taken in CELL order (the grid's sorted copy; .w = original index): consecutive warps then probe the
@@ -258,7 +453,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, TOP32 ? 8 : 4) k_knn_cov(const
         double cu = 0.0;
         if (TOP32) {
             u64 mine;
-            c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
+            const bool fast = warp_knn_select32(g, p.x, p.y, p.z, r2, max_nn, lane, buf, shist[warp], &mine, &c);
+            if (!fast) c = warp_knn_top32(g, p.x, p.y, p.z, r2, max_nn, lane, &mine);
+            if (stats && lane == 0) atomicAdd(stats + (fast ? 0 : 1), 1u);  // PCR_DEBUG only
             // lane k fetches neighbour k (all gathers in flight together) and writes its nine products to shared
             // memory; lane l < 9 then adds column l in neighbour order (the reference's sequential cumulants)
             double *prod = reinterpret_cast<double *>(buf);
@@ -590,18 +787,31 @@ int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int 
         return pcr_fail(ctx, PCR_ERR_INVALID, "normals: radius must be > 0 and 1 <= max_nn <= %d", KNN_CAP / 2);
     if (n == 0) return PCR_OK;
     Grid g;
-    // The register top-32 search also handles finer cells (2 rings); measured on the 100k-point cloud that is SLOWER
-    // (0.97 vs 0.83 ms per alignment: more, shorter rows — the per-row latency dominates), so 1 ring is the default.
-    static const int rings = getenv("PCR_KNN_RINGS") ? atoi(getenv("PCR_KNN_RINGS")) : 1;
+    // Half-radius cells (2 rings): warp_knn_select32 usually finds the max_nn nearest neighbours inside the central 3x3x3
+    // block and never touches the other 98 cells.  (With the round-1 streaming list alone 2 rings were slower — one round
+    // trip per row, 25 rows; the new path fetches all row ranges at once.)  PCR_KNN_RINGS=1 keeps radius-sized cells.
+    static const int rings = getenv("PCR_KNN_RINGS") ? atoi(getenv("PCR_KNN_RINGS")) : 2;
     PCR_TRY(pcr_grid_build_rings(ctx, pts, n, radius, (max_nn <= 32 && rings == 2) ? 2 : 1, nullptr, nullptr, &g));
     PCR_ALLOC(cov, double, (size_t)n * 6);
     {
         KScope ks(ctx, KC_KNN_COV, 32.0 * n + 48.0 * n);
+        unsigned int *stats = nullptr;
+        static const bool dbg = getenv("PCR_DEBUG") != nullptr;
+        if (dbg) {
+            stats = arena<unsigned int>(ctx, 2);
+            if (stats) cudaMemsetAsync(stats, 0, 8, ctx->stream);
+        }
         if (max_nn <= 32)
-            k_knn_cov<true><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+            k_knn_cov<true><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov, stats);
         else
-            k_knn_cov<false><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov);
+            k_knn_cov<false><<<knn_blocks(ctx, n), KNN_WARPS * 32, 0, ctx->stream>>>(pts, n, g, (float)(radius * radius), max_nn, cov, stats);
         PCR_LAUNCHED();
+        if (stats) {
+            unsigned int h[2] = {0, 0};
+            cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[pcr] knn_cov n=%d max_nn=%d: histogram-select %u, streaming list %u\n", n, max_nn, h[0], h[1]);
+        }
     }
     {
         KScope ks(ctx, KC_NORMALS_SOLVE, 48.0 * n + 16.0 * n);
