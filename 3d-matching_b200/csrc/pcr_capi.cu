@@ -358,6 +358,11 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     return PCR_OK;
 }
 
+int pcr_align_device_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, const pcr_align_params *p,
+                          pcr_align_result *res) {
+    return align_device(ctx, src, ns, tgt, nt, p, res);
+}
+
 extern "C" {
 
 int pcr_align(pcr_ctx *ctx, const float *src, int ns, const float *tgt, int nt, const pcr_align_params *p,

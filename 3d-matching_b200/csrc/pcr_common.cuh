@@ -131,6 +131,7 @@ struct pcr_ctx {
     pcr_ctx *helper = nullptr;
     struct Worker *worker = nullptr;
     bool owns_stream = false;
+    void *dist = nullptr;              // multi-GPU state (pcr_dist.cu): NCCL communicator, exchange buffers, worker contexts
     cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
 };
 

@@ -167,6 +167,8 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
     return PCR_OK;
 }
 
+void pcr_dist_free(pcr_ctx *ctx);  // pcr_dist.cu
+
 extern "C" {
 
 int pcr_version(void) { return 100; }
@@ -205,6 +207,7 @@ int pcr_destroy(pcr_ctx *ctx) {
         delete ctx->worker;
     }
     if (ctx->helper) pcr_destroy(ctx->helper);
+    pcr_dist_free(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (void *b : ctx->blocks) cudaFree(b);
     for (void *b : ctx->rsess.bufs)

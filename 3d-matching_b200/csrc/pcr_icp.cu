@@ -34,6 +34,7 @@ struct IcpState {
     long long dbgmax[64];  // per-pass slowest CTA loop
     long long dbgfin[64];  // per-pass slowest CTA finish
     long long dbgp[64];  // per-pass loop cycles of CTA 0 (first 64 passes)
+    long long dbg2[4];   // PCR_ICP_TRACE: inside the end-of-pass logic of CTA 0 — LDL^T, sin/cos + update, compose
     long long dbg[4];  // clock cycles of CTA 0: point loop, reduction + barrier, end-of-pass logic (PCR_ICP_TRACE=1 prints them)
 };
 
@@ -89,6 +90,7 @@ struct IcpLocal {
     double prev_fit, prev_rmse, fitness, rmse;
     long long count, sumq;
     int pass, done, iterations, converged;
+    long long tdbg[3];
 };
 
 // end-of-pass logic (ONE thread per CTA): convergence test, 6x6 solve, Euler-ZYX update, T <- U T.
@@ -119,9 +121,13 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
         L->prev_rmse = rmse;
         double U[16];
         for (int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        const long long t0 = clock64();
+        long long t1 = t0, t2 = t0;
         if (cnt > 0) {
             double x[6];
-            if (ldlt6_solve_dev(fA, fb, x) == 0) {
+            const int rc = ldlt6_solve_dev(fA, fb, x);
+            t1 = clock64();
+            if (rc == 0) {
                 double sa, ca, sb, cb, sg, cg;
                 pcr_sincos(x[0], &sa, &ca);
                 pcr_sincos(x[1], &sb, &cb);
@@ -130,6 +136,7 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
                 U[4] = cb * sg;  U[5] = (sa * sb) * sg + ca * cg;  U[6] = (ca * sb) * sg - sa * cg;  U[7] = x[4];
                 U[8] = -sb;      U[9] = sa * cb;                   U[10] = ca * cb;                  U[11] = x[5];
             }
+            t2 = clock64();
         }
         double Tn[16];
         for (int i = 0; i < 3; i++)
@@ -142,6 +149,7 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
         Tn[15] = 1.0;
         for (int i = 0; i < 16; i++) L->T[i] = Tn[i];
         L->iterations = pass + 1;
+        L->tdbg[0] = t1 - t0; L->tdbg[1] = t2 - t1; L->tdbg[2] = clock64() - t2;
     }
     L->pass = pass + 1;
 }
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
             S->dbg[1] += c2 - c1;
             S->dbg[3] += ce - cb;
             S->dbg[2] += clock64() - c2;
+            for (int i = 0; i < 3; i++) S->dbg2[i] += L.tdbg[i];
         }
         if (L.done) break;
     }
@@ -623,6 +632,8 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
             fprintf(stderr, "\n[pcr icp] slowest CTA finish per pass:");
             for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgfin[i]);
             fprintf(stderr, "  barrier alone %.0f\n", (double)hS->dbg[3] / hS->pass);
+            fprintf(stderr, "[pcr icp] end-of-pass logic of CTA 0, cycles per pass: LDL^T %.0f  sin/cos + update %.0f  compose %.0f\n",
+                    (double)hS->dbg2[0] / hS->pass, (double)hS->dbg2[1] / hS->pass, (double)hS->dbg2[2] / hS->pass);
         }
         // passes that did work (the rest returned at the `done` check): iterations + 1
         if (ctx->profiling && pend_idx < ctx->pending.size()) ctx->pending[pend_idx].launches = hS->pass;

@@ -102,6 +102,7 @@ EXPORTS = [
     "pcr_ransac_step", "pcr_inlier_count",
     "pcr_icp_point_to_plane",
     "pcr_align_default_params", "pcr_align", "pcr_align_host", "pcr_align_files",
+    "pcr_comm_unique_id", "pcr_comm_init", "pcr_comm_destroy", "pcr_ransac_multi", "pcr_align_batch",
     "pcr_ply_probe", "pcr_ply_read", "pcr_ply_write",
 ]
 

@@ -305,6 +305,72 @@ class Engine:
                                                   C.c_int(int(squared)), _ptr(out)))
         return out
 
+    # ---- multi-GPU on the C side (pcr_dist.cu): NCCL communicator owned by the context ------------------------------
+    def comm_init(self, group=None) -> int:
+        """Create the context's NCCL communicator over the ranks of the (already initialised) torch.distributed group:
+        rank 0 draws the id, torch.distributed only carries its 128 bytes.  Returns the world size (1: nothing to do)."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            with self._lock:
+                self._check(self.lib.pcr_comm_init(self.ctx, None, C.c_int(0), C.c_int(0), C.c_int(1)))
+            return 1
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        idb = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self.lib.pcr_comm_unique_id(idb, C.c_int(128))
+            if rc != 0:
+                raise RuntimeError(f"pcr_comm_unique_id failed ({rc}): is libnccl.so.2 loadable?")
+        if dist.get_backend(group) == "nccl":
+            t = torch.tensor(list(idb), dtype=torch.uint8, device=self.tdev)
+        else:
+            t = torch.tensor(list(idb), dtype=torch.uint8)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().tolist())
+        buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        with self._lock:
+            self._check(self.lib.pcr_comm_init(self.ctx, buf, C.c_int(128), C.c_int(rank), C.c_int(world)))
+        return world
+
+    def comm_destroy(self) -> None:
+        with self._lock:
+            self._check(self.lib.pcr_comm_destroy(self.ctx))
+
+    def ransac_multi(self, src, tgt, corr, max_dist: float, max_iter: int, confidence: float = 0.999, seed: int = 0,
+                     edge_sim: float = 0.9, first_wave: int = 0, growth: int = 0):
+        """RANSAC sharded over the ranks of the context's communicator (pcr_ransac_multi; the whole wave loop, the
+        exchange and the replay run in C).  Every rank passes the same inputs and gets the same result.
+        Returns (DeviceRegResult, waves)."""
+        self._need_xyzw(src, "source")
+        self._need_xyzw(tgt, "target")
+        self._need_corr(corr)
+        r = _capi.RegResult()
+        nw = C.c_int(0)
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_ransac_multi(self.ctx, _ptr(src), C.c_int(src.shape[0]), _ptr(tgt), C.c_int(tgt.shape[0]),
+                                                  _ptr(corr), C.c_int(corr.shape[0]), C.c_double(max_dist), C.c_double(edge_sim),
+                                                  C.c_int64(max_iter), C.c_double(confidence), C.c_uint64(seed),
+                                                  C.c_int64(first_wave), C.c_int(growth), C.byref(r), C.byref(nw)))
+        return DeviceRegResult.from_c(r), nw.value
+
+    def align_batch(self, local_pairs, params: _capi.AlignParams, n_total: int, workers: int = 1) -> np.ndarray:
+        """pcr_align_batch: this rank's pairs (packed CUDA tensors, global pair index rank, rank + world, ...) aligned by
+        `workers` native threads; returns the (n_total, 18) float64 table of ALL pairs (identical on every rank)."""
+        n = len(local_pairs)
+        for s, t in local_pairs:
+            self._need_xyzw(s, "source")
+            self._need_xyzw(t, "target")
+        sp = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s, _ in local_pairs])
+        tp = (C.c_void_p * max(n, 1))(*[t.data_ptr() for _, t in local_pairs])
+        ns = (C.c_int * max(n, 1))(*[int(s.shape[0]) for s, _ in local_pairs])
+        nt = (C.c_int * max(n, 1))(*[int(t.shape[0]) for _, t in local_pairs])
+        out = np.zeros((max(n_total, 1), 18), np.float64)
+        with self._lock:
+            self._bind_stream()
+            self._check(self.lib.pcr_align_batch(self.ctx, C.c_int(n), sp, ns, tp, nt, C.byref(params), C.c_int(workers),
+                                                 C.c_int(n_total), out.ctypes.data_as(C.c_void_p)))
+        return out[:n_total]
+
     # ---- ICP -------------------------------------------------------------------------------------------
     def icp_point_to_plane(self, src, tgt, tgt_normals, max_dist: float, init=None, max_iter: int = 30,
                            rel_fitness: float = 1e-6, rel_rmse: float = 1e-6, want_corr: bool = True):

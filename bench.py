@@ -185,6 +185,7 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pcr_b200.engine import get_engine
     eng = get_engine(local)
+    eng.comm_init()  # the context's own NCCL communicator (pcr_comm_init): the sharded legs exchange on the C side
     peaks = load_peaks()
 
     # Weak scaling = the SAME work on every GPU: all ranks align the same pair (different pairs differ by up to 2x in
@@ -546,7 +547,6 @@ def run_aux(eng, args, world, rank, peaks):
     import torch
     import torch.distributed as dist
     from pcr_b200 import synth
-    from pcr_b200.dist import ransac_multi_gpu
     out = {}
     v = VOXEL
     src, tgt, _ = make_pair(SEED_PAIR)  # every rank holds the SAME clouds for the sharded RANSAC
@@ -556,13 +556,14 @@ def run_aux(eng, args, world, rank, peaks):
     sf, tf = eng.compute_fpfh(sd, sn, 5 * v, 100), eng.compute_fpfh(td, tn, 5 * v, 100)
     corr = eng.match_features(sf, tf, True).contiguous()
     H = args.ransac_hyps
-    ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, H, 1.0, 7)  # warm-up at full size: the scratch arena grows here, not in the timed call
+    # pcr_ransac_multi: wave loop, per-wave ncclAllGather and replay all on the C side of the boundary
+    eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)  # warm-up at full size: the scratch arena grows here, not in the timed call
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    r, st = ransac_multi_gpu(eng, sd, td, corr, 1.5 * v, H, 1.0, 7)
+    r, n_waves = eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
@@ -572,7 +573,7 @@ def run_aux(eng, args, world, rank, peaks):
         ms = float(t.item())
     out["ransac"] = {"hypotheses": H, "ms": ms, "hyp_per_s": H / (ms * 1e-3), "survivors": r.survivors,
                      "checker_pass_rate": r.survivors / H, "best_hyp": r.best_hyp, "inlier_count": r.inlier_count,
-                     "waves": st["waves"], "n_gpus": world}
+                     "waves": n_waves, "n_gpus": world, "driver": "pcr_ransac_multi (C, NCCL all-gather per wave)"}
     # cfg4 parity: the CPU oracle's sequential loop over the same 10M hypotheses, run once offline (368 s on 8 cores) and
     # committed (tests/golden/cfg4_ransac_10m.json, made by tests/golden/make_cfg4_golden.py); the sharded run must
     # reproduce it at every GPU count — winner, counts, fixed-point sum, every bit of T, survivors, consumed iterations
@@ -592,29 +593,26 @@ def run_aux(eng, args, world, rank, peaks):
         out["ransac"]["identical_to_oracle_golden_10m"] = f"golden unreadable: {e}"
     # batch of independent pairs (config 5 style: 50k-point pairs, full pipeline, reference-default criteria), pair i ->
     # rank i mod world, no communication until the final all-gather of 18 doubles per pair
-    from pcr_b200.dist import align_batch
     B = args.batch_pairs
     if B > 0:
         pairs, host_pairs = [], {}
-        for i in range(B * world):
-            if i % world == rank:
-                s_i, t_i, _ = synth.make_pair(50000, v, 30000 + i)
-                pairs.append((eng.pack(s_i), eng.pack(t_i)))
-                if rank == 0 and len(host_pairs) < args.batch_check and not args.no_cpu:
-                    host_pairs[i] = (s_i, t_i)
-            else:
-                pairs.append(None)
+        for i in range(rank, B * world, world):  # this rank's pairs: global index rank, rank + world, ...
+            s_i, t_i, _ = synth.make_pair(50000, v, 30000 + i)
+            pairs.append((eng.pack(s_i), eng.pack(t_i)))
+            if rank == 0 and len(host_pairs) < args.batch_check and not args.no_cpu:
+                host_pairs[i] = (s_i, t_i)
         pb = eng.default_params(v)
         pb.ransac_max_iter = RANSAC_ITERS
         pb.seed = 7
-        batch = {"pairs": B * world, "points_per_cloud": 50000, "criteria": "confidence 0.999, ICP 30 iterations / 1e-6"}
+        batch = {"pairs": B * world, "points_per_cloud": 50000, "criteria": "confidence 0.999, ICP 30 iterations / 1e-6",
+                 "driver": "pcr_align_batch (C: native worker threads, one final ncclAllGather)"}
         for workers in (1, 3):
-            align_batch(eng, pairs, pb, workers=workers)  # warm-up (worker contexts, arenas)
+            eng.align_batch(pairs, pb, B * world, workers=workers)  # warm-up (worker contexts, arenas)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            tab = align_batch(eng, pairs, pb, workers=workers)
+            tab = eng.align_batch(pairs, pb, B * world, workers=workers)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if world > 1:

@@ -221,6 +221,32 @@ PCR_API int pcr_align_host(pcr_ctx *ctx, const float *src_xyz_host, int ns, cons
 PCR_API int pcr_align_files(pcr_ctx *ctx, const char *src_path, const char *tgt_path, const pcr_align_params *p,
                             pcr_align_result *result_host);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (nothing in the reference: it is single-process) ----
+ * The hypothesis space of one RANSAC and batches of independent pairs shard over the GPUs of a box; single-pair ICP does
+ * not ("replicas only").  NCCL is bound at run time (dlopen of libnccl.so.2; PCR_NCCL_LIB overrides), so programs that
+ * stay on one GPU need no NCCL at all, and with world == 1 / no communicator every call below is the single-GPU path.
+ *   rank 0:      pcr_comm_unique_id(id, 128)      -> hand the 128 bytes to the other ranks (MPI, torch.distributed, a file ...)
+ *   every rank:  pcr_comm_init(ctx, id, 128, rank, world)
+ * pcr_ransac_multi: every rank passes the SAME clouds and correspondences; hypotheses [0, max_iter) are scored in waves
+ * cut into per-rank slices, one fixed-size ncclAllGather per wave exchanges the prefix maxima, and every rank replays the
+ * sequential loop: the result is bit-identical on every rank, for every world size, and to pcr_ransac.
+ * first_wave (hypotheses per rank of the first, unpruned wave; <= 0: 2048) and growth (wave size factor; < 2: 8) only
+ * change the schedule, never the result.  *n_waves_host (optional) = waves executed.
+ * pcr_align_batch: pair i of n_total belongs to rank i % world; the caller passes ITS n_local pairs in that order
+ * (device clouds).  The rank aligns them with `workers` host threads (own context and stream each; 1 = sequential) and
+ * one final all-gather fills out_host (n_total x 18 doubles: 16 transform entries, fitness, inlier RMSE) on every rank. */
+#define PCR_COMM_ID_BYTES 128
+PCR_API int pcr_comm_unique_id(void *id_out_host, int bytes);
+PCR_API int pcr_comm_init(pcr_ctx *ctx, const void *id_host, int bytes, int rank, int world);
+PCR_API int pcr_comm_destroy(pcr_ctx *ctx);
+PCR_API int pcr_ransac_multi(pcr_ctx *ctx, const float *src_xyzw_dev, int ms, const float *tgt_xyzw_dev, int mt,
+                             const int *corr_dev, int c, double max_dist, double edge_sim, int64_t max_iter,
+                             double confidence, uint64_t seed, int64_t first_wave, int growth,
+                             pcr_reg_result *result_host, int *n_waves_host);
+PCR_API int pcr_align_batch(pcr_ctx *ctx, int n_local, const float *const *src_xyzw_dev, const int *ns,
+                            const float *const *tgt_xyzw_dev, const int *nt, const pcr_align_params *p, int workers,
+                            int n_total, double *out_host);
+
 /* ---- PLY files (host only; no context, no device work) ------------------------------------------------------
  * Replaces o3d.io.read_point_cloud (src/ply/ply.py:80) and o3d.io.write_point_cloud (trim_ply.py:40; the
  * reference's converter writes ASCII PLY, convert_stl-ply.py:8).  Formats: ascii, binary_little_endian,

@@ -176,3 +176,40 @@ print("cold ok")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "cold ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_c_side_sharding_entry_points_on_one_gpu(orc, eng):
+    """pcr_ransac_multi / pcr_align_batch without a communicator (world 1) are the single-GPU paths: same result as
+    pcr_ransac / as aligning the pairs one by one, for any wave schedule and any number of native workers."""
+    v = 0.005
+    src, tgt, _ = synth.make_pair(20000, v, 20241)
+    S, G = orc.preprocess(src, v, full_normals=False), orc.preprocess(tgt, v, full_normals=False)
+    corr = orc.match_features(S.pcd_fpfh, G.pcd_fpfh, True)
+    sd, td = eng.pack(S.pcd_down), eng.pack(G.pcd_down)
+    dc = torch.from_numpy(np.ascontiguousarray(corr, np.int32)).to(eng.tdev)
+    eng.comm_init()
+    for conf, iters in ((0.999, 100000), (1.0, 30000)):
+        want = orc.ransac(S.pcd_down, G.pcd_down, corr, 1.5 * v, iters, conf, seed=3)
+        for first, growth in ((0, 0), (512, 2), (100000, 8)):
+            got, waves = eng.ransac_multi(sd, td, dc, 1.5 * v, iters, conf, 3, first_wave=first, growth=growth)
+            assert (got.best_hyp, got.inlier_count, got.sum_d2_fixed, got.hyp_evaluated) == \
+                   (want.best_hyp, want.inlier_count, want.sum_d2_fixed, want.hyp_evaluated), (conf, first, growth)
+            if conf == 1.0:  # with an early exit the engine has scored (and counts) whole waves, the oracle 103 hypotheses
+                assert got.survivors == want.survivors
+            assert np.array_equal(got.transformation, want.transformation) and waves >= 1
+    with pytest.raises(ValueError, match="indexes outside"):
+        eng.ransac_multi(sd, td, torch.tensor([[0, 0], [1, 1], [2, 10 ** 6]], dtype=torch.int32, device=eng.tdev), 1.5 * v, 100)
+    pairs = []
+    for i in range(5):
+        s, t, _ = synth.make_pair(12000, v, 700 + i)
+        pairs.append((eng.pack(s), eng.pack(t)))
+    p = eng.default_params(v)
+    p.ransac_max_iter = 20000
+    p.seed = 3
+    one = np.stack([np.concatenate([np.asarray(r.icp.transformation), [r.icp.fitness, r.icp.inlier_rmse]])
+                    for r in (eng.align_device(s, t, p) for s, t in pairs)])
+    for workers in (1, 3, 8):
+        assert np.array_equal(eng.align_batch(pairs, p, len(pairs), workers=workers), one), workers
+    assert eng.align_batch([], p, 0).shape == (0, 18)
+    with pytest.raises(ValueError):
+        eng.align_batch(pairs[:2], p, 5)  # this rank must hold 5 of 5 pairs
