@@ -593,6 +593,15 @@ int pcr_ply_probe(const char *path, pcr_ply_info *info, char *err, int err_cap) 
         if (!path || !info) fail(PCR_ERR_INVALID, "null argument");
         Mapped f(path);
         Header h = parse_header(f);
+        // A header may claim any vertex count: callers size (and pin) their buffers from it, so a count the file cannot
+        // hold is rejected here, before anything is allocated.  Binary: stride bytes per vertex; ASCII: at
+        // least two bytes ("0\n") per property of a vertex line would be generous — one byte per vertex is the safe floor.
+        const Element &v = h.elements[h.vertex];
+        const size_t avail = f.n > h.data_offset ? f.n - h.data_offset : 0;
+        const double need = h.format == 0 ? (double)v.count : (double)v.count * (double)v.stride;
+        if (need > (double)avail)
+            fail(PCR_ERR_INVALID, "header declares " + std::to_string(v.count) + " vertices but only " + std::to_string(avail) +
+                                      " bytes follow it (truncated file)");
         fill_info(h, info);
     });
 }

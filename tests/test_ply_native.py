@@ -359,3 +359,23 @@ def test_reader_is_reentrant_across_threads(tmp_path):
     for t in th:
         t.join()
     assert not bad, bad
+
+
+def test_probe_rejects_a_vertex_count_the_file_cannot_hold(tmp_path):
+    """readers allocate (pinned) memory from the header's vertex count; a count that the file's size rules out
+    must fail in pcr_ply_probe, before anything is allocated."""
+    import ctypes as C
+    from pcr_b200 import _capi
+    lib = _capi.load()
+    info = _capi.PlyInfo()
+    err = C.create_string_buffer(256)
+    hdr = b"ply\nformat binary_little_endian 1.0\nelement vertex 4000000000\nproperty float x\nproperty float y\nproperty float z\nend_header\n"
+    f = tmp_path / "huge.ply"
+    f.write_bytes(hdr + b"\0" * 48)
+    assert lib.pcr_ply_probe(str(f).encode(), C.byref(info), err, 256) == _capi.PCR_ERR_INVALID and b"4000000000" in err.value
+    g = tmp_path / "huge_ascii.ply"
+    g.write_bytes(hdr.replace(b"binary_little_endian", b"ascii") + b"0 0 0\n")
+    assert lib.pcr_ply_probe(str(g).encode(), C.byref(info), err, 256) == _capi.PCR_ERR_INVALID
+    ok = tmp_path / "ok.ply"
+    ok.write_bytes(hdr.replace(b"4000000000", b"4") + b"\0" * 48)
+    assert lib.pcr_ply_probe(str(ok).encode(), C.byref(info), err, 256) == 0 and info.n_vertex == 4
