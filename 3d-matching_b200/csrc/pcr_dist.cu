@@ -234,9 +234,10 @@ int pcr_ransac_multi(pcr_ctx *ctx, const float *src_, int ms, const float *tgt_,
     PCR_TRY(pcr_corr_check_impl(ctx, corr, c, ms, mt));
     RansacWork w;
     PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
-    // measured at 10M hypotheses (tools/gpu_dist_check.py): (4096, x4) 32.6 / 18.2 ms on 1 / 2 GPUs, (2048, x8) 30.3 / 15.0 ms
-    if (first_wave <= 0) first_wave = 2048;
-    if (growth < 2) growth = 8;
+    // measured at 10M hypotheses (tools/gpu_dist_check.py), ms on 1 / 2 / 8 GPUs: (4096, x4) 32.6 / 18.2 / -,
+    // (2048, x8) 28.6 / 15.0 / 4.88, (16384, x4) 28.7 / 15.0 / 4.43
+    if (first_wave <= 0) first_wave = 16384;
+    if (growth < 2) growth = 4;
     const int64_t max_wave = (int64_t)1 << 22;
     int64_t begin = 0, wave = first_wave * world, survivors = 0;
     int waves = 0;

@@ -557,23 +557,29 @@ def run_aux(eng, args, world, rank, peaks):
     corr = eng.match_features(sf, tf, True).contiguous()
     H = args.ransac_hyps
     # pcr_ransac_multi: wave loop, per-wave ncclAllGather and replay all on the C side of the boundary
-    eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)  # warm-up at full size: the scratch arena grows here, not in the timed call
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    r, n_waves = eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    for _ in range(2):  # warm-up at full size: the scratch arena and the exchange buffers grow here, NCCL sets its channels up
+        eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)
+    runs = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r, n_waves = eng.ransac_multi(sd, td, corr, 1.5 * v, H, 1.0, 7)
+        b.record()
+        torch.cuda.synchronize()
+        t_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([t_ms], dtype=torch.float64, device=eng.tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        runs.append(t_ms)
+    ms = float(np.median(runs))  # max over ranks per run, median of three runs (all three are reported)
     out["ransac"] = {"hypotheses": H, "ms": ms, "hyp_per_s": H / (ms * 1e-3), "survivors": r.survivors,
                      "checker_pass_rate": r.survivors / H, "best_hyp": r.best_hyp, "inlier_count": r.inlier_count,
-                     "waves": n_waves, "n_gpus": world, "driver": "pcr_ransac_multi (C, NCCL all-gather per wave)"}
+                     "waves": n_waves, "n_gpus": world, "driver": "pcr_ransac_multi (C, NCCL all-gather per wave)",
+                     "ms_of_each_run_max_over_ranks": runs}
     # cfg4 parity: the CPU oracle's sequential loop over the same 10M hypotheses, run once offline (368 s on 8 cores) and
     # committed (tests/golden/cfg4_ransac_10m.json, made by tests/golden/make_cfg4_golden.py); the sharded run must
     # reproduce it at every GPU count — winner, counts, fixed-point sum, every bit of T, survivors, consumed iterations

@@ -230,7 +230,7 @@ PCR_API int pcr_align_files(pcr_ctx *ctx, const char *src_path, const char *tgt_
  * pcr_ransac_multi: every rank passes the SAME clouds and correspondences; hypotheses [0, max_iter) are scored in waves
  * cut into per-rank slices, one fixed-size ncclAllGather per wave exchanges the prefix maxima, and every rank replays the
  * sequential loop: the result is bit-identical on every rank, for every world size, and to pcr_ransac.
- * first_wave (hypotheses per rank of the first, unpruned wave; <= 0: 2048) and growth (wave size factor; < 2: 8) only
+ * first_wave (hypotheses per rank of the first, unpruned wave; <= 0: 16384) and growth (wave size factor; < 2: 4) only
  * change the schedule, never the result.  *n_waves_host (optional) = waves executed.
  * pcr_align_batch: pair i of n_total belongs to rank i % world; the caller passes ITS n_local pairs in that order
  * (device clouds).  The rank aligns them with `workers` host threads (own context and stream each; 1 = sequential) and
