@@ -186,6 +186,31 @@ static int exclusive_scan_impl(pcr_ctx *ctx, T *data, long long n) {
 }
 
 int pcr_exclusive_scan_u32(pcr_ctx *ctx, uint32_t *data, long long n) { return exclusive_scan_impl<uint32_t>(ctx, data, n); }
+
+// Counting-sort tables in ONE allocation cleared by ONE memset: [ncells + 1 counters / starts][scan state: tiles flags + ticket].
+// (Round 1 cleared `start`, a second per-cell `fill` array and the scan state separately: three memsets per grid, ~10 grids
+// per alignment.)
+struct SortTables {
+    uint32_t *start;
+    unsigned long long *state;
+    int tiles;
+};
+static int sort_tables_alloc(pcr_ctx *ctx, long long ncells, SortTables *t) {
+    t->tiles = div_up(ncells, 4096);
+    const size_t start_bytes = ((sizeof(uint32_t) * ((size_t)ncells + 1)) + 15) & ~(size_t)15;
+    const size_t bytes = start_bytes + sizeof(unsigned long long) * ((size_t)t->tiles + 1);
+    unsigned char *base = arena<unsigned char>(ctx, bytes);
+    if (!base) return PCR_ERR_OOM;
+    t->start = reinterpret_cast<uint32_t *>(base);
+    t->state = reinterpret_cast<unsigned long long *>(base + start_bytes);
+    PCR_CUDA(cudaMemsetAsync(base, 0, bytes, ctx->stream));
+    return PCR_OK;
+}
+static int sort_tables_scan(pcr_ctx *ctx, const SortTables &t, long long ncells) {
+    k_scan_onepass<uint32_t><<<t.tiles, 1024, 0, ctx->stream>>>(t.start, ncells, t.state, (unsigned int *)(t.state + t.tiles));
+    PCR_LAUNCHED();
+    return PCR_OK;
+}
 int pcr_exclusive_scan_u64(pcr_ctx *ctx, unsigned long long *data, long long n) {
     return exclusive_scan_impl<unsigned long long>(ctx, data, n);
 }
@@ -206,25 +231,26 @@ __device__ __forceinline__ uint32_t cell_of(const GridDims &g, const float4 &p) 
     return (uint32_t)((cz * g.ny + cy) * g.nx + cx);
 }
 
+// cell[i] = cell of point i, rank[i] = its arrival rank inside the cell (the value the counter had)
 __global__ void __launch_bounds__(256) k_cell_count(const float4 *__restrict__ pts, int n, GridDims g,
-                                                    uint32_t *__restrict__ cell, uint32_t *__restrict__ count) {
+                                                    uint32_t *__restrict__ cell, uint32_t *__restrict__ rank,
+                                                    uint32_t *__restrict__ count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = cell_of(g, __ldg(pts + i));
     cell[i] = c;
-    atomicAdd(count + c, 1u);
+    rank[i] = atomicAdd(count + c, 1u);
 }
 
-// pos = start[c] + (number of points of cell c placed before): the slot order inside a cell follows the atomic
-// arrival order, which no result depends on (ties are broken by original index, sums are fixed point).
+// pos = start[c] + rank: the slot order inside a cell follows the atomic arrival order of the counting pass, which no
+// result depends on (ties are broken by original index, sums are fixed point).
 __global__ void __launch_bounds__(256) k_cell_scatter(const float4 *__restrict__ pts, int n,
-                                                      const uint32_t *__restrict__ cell,
-                                                      const uint32_t *__restrict__ start, uint32_t *__restrict__ fill,
-                                                      float4 *__restrict__ sorted) {
+                                                      const uint32_t *__restrict__ cell, const uint32_t *__restrict__ rank,
+                                                      const uint32_t *__restrict__ start, float4 *__restrict__ sorted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = cell[i];
-    const uint32_t pos = start[c] + atomicAdd(fill + c, 1u);
+    const uint32_t pos = start[c] + rank[i];
     float4 p = __ldg(pts + i);
     p.w = __int_as_float(i);
     sorted[pos] = p;
@@ -261,17 +287,17 @@ int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, 
     }
     const long long ncells = nx * ny * nz;
     GridDims gd{(double)lo[0], (double)lo[1], (double)lo[2], 1.0 / h, (int)nx, (int)ny, (int)nz};
-    PCR_ALLOC(cell, uint32_t, (size_t)n);
-    PCR_ALLOC(start, uint32_t, (size_t)ncells + 1);
-    PCR_ALLOC(fill, uint32_t, (size_t)ncells);
+    PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
+    uint32_t *rank = cell + n;
     PCR_ALLOC(sorted, float4, (size_t)n);
-    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 16.0 * (double)ncells);
-    PCR_CUDA(cudaMemsetAsync(start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), ctx->stream));
-    PCR_CUDA(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)ncells, ctx->stream));
-    k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, start);
+    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
+    SortTables tb;
+    PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
+    uint32_t *start = tb.start;
+    k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, rank, start);
     PCR_LAUNCHED();
-    PCR_TRY(pcr_exclusive_scan_u32(ctx, start, ncells));
-    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, start, fill, sorted);
+    PCR_TRY(sort_tables_scan(ctx, tb, ncells));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());
     g->sorted = sorted;
@@ -301,7 +327,8 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 8 bits -> every th
 }
 
 __global__ void __launch_bounds__(256) k_morton_count(const float4 *__restrict__ pts, int n, MortonDims g,
-                                                      uint32_t *__restrict__ cell, uint32_t *__restrict__ count) {
+                                                      uint32_t *__restrict__ cell, uint32_t *__restrict__ rank,
+                                                      uint32_t *__restrict__ count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = __ldg(pts + i);
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(256) k_morton_count(const float4 *__restrict__
     const int cz = min(max((int)floor(((double)p.z - g.oz) * g.inv_c), 0), g.lim);
     const uint32_t c = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
     cell[i] = c;
-    atomicAdd(count + c, 1u);
+    rank[i] = atomicAdd(count + c, 1u);
 }
 
 int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out) {
@@ -326,17 +353,17 @@ int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorte
     while (L < 8 && (1LL << (3 * L)) < 4LL * n) L++;
     const long long ncells = 1LL << (3 * L);
     MortonDims md{(double)lo[0], (double)lo[1], (double)lo[2], ext > 0.0 ? (double)(1 << L) / (ext * (1.0 + 1e-6)) : 0.0, (1 << L) - 1};
-    PCR_ALLOC(cell, uint32_t, (size_t)n);
-    PCR_ALLOC(start, uint32_t, (size_t)ncells + 1);
-    PCR_ALLOC(fill, uint32_t, (size_t)ncells);
+    PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
+    uint32_t *rank = cell + n;
     PCR_ALLOC(sorted, float4, (size_t)n);
-    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 16.0 * (double)ncells);
-    PCR_CUDA(cudaMemsetAsync(start, 0, sizeof(uint32_t) * ((size_t)ncells + 1), ctx->stream));
-    PCR_CUDA(cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)ncells, ctx->stream));
-    k_morton_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, md, cell, start);
+    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
+    SortTables tb;
+    PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
+    uint32_t *start = tb.start;
+    k_morton_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, md, cell, rank, start);
     PCR_LAUNCHED();
-    PCR_TRY(pcr_exclusive_scan_u32(ctx, start, ncells));
-    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, start, fill, sorted);
+    PCR_TRY(sort_tables_scan(ctx, tb, ncells));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
     PCR_LAUNCHED();
     PCR_CUDA(cudaGetLastError());
     *sorted_out = sorted;
