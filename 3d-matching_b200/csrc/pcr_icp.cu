@@ -38,45 +38,55 @@ struct IcpState {
     long long dbg[4];  // clock cycles of CTA 0: point loop, reduction + barrier, end-of-pass logic (PCR_ICP_TRACE=1 prints them)
 };
 
-__device__ __forceinline__ int ldlt6_solve_dev(const double (*A)[6], const double *b, double *x) {
-    double L[6][6], d[6], y[6];
-    bool bad = false;
+// 6x6 SPD solve, rule D8 (round 2; the same operations in the same order as oracle/pcr_oracle.c: solve6_block): block
+// elimination over the rotation / translation 3x3 blocks with closed-form symmetric 3x3 inverses.  Two fp64 divisions on
+// the critical path instead of the six pivots (21 divisions) of the unpivoted LDL^T it replaces — the solve runs on one
+// thread per CTA while the whole GPU waits for the next transform.
+__device__ __forceinline__ int inv3_sym_dev(const double *m /* 00 01 02 11 12 22 */, double *o) {
+    const double c00 = m[3] * m[5] - m[4] * m[4];
+    const double c01 = m[2] * m[4] - m[1] * m[5];
+    const double c02 = m[1] * m[4] - m[2] * m[3];
+    const double det = (m[0] * c00 + m[1] * c01) + m[2] * c02;
+    if (!(det > 0.0) || isinf(det)) return -1;
+    const double c11 = m[0] * m[5] - m[2] * m[2];
+    const double c12 = m[1] * m[2] - m[0] * m[4];
+    const double c22 = m[0] * m[3] - m[1] * m[1];
+    const double id = 1.0 / det;
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id; o[3] = c11 * id; o[4] = c12 * id; o[5] = c22 * id;
+    return 0;
+}
+
+__device__ __forceinline__ int solve6_block_dev(const double (*A)[6], const double *b, double *x) {
+    const double P[6] = {A[0][0], A[0][1], A[0][2], A[1][1], A[1][2], A[2][2]};
+    double Pi[6];
+    if (inv3_sym_dev(P, Pi) != 0) return -1;
+    const double PiF[3][3] = {{Pi[0], Pi[1], Pi[2]}, {Pi[1], Pi[3], Pi[4]}, {Pi[2], Pi[4], Pi[5]}};
+    double W[3][3];  // W = Q Pi, Q[i][k] = A[3 + i][k]
 #pragma unroll
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) L[i][j] = 0.0;
+        for (int j = 0; j < 3; j++) W[i][j] = (A[3 + i][0] * PiF[0][j] + A[3 + i][1] * PiF[1][j]) + A[3 + i][2] * PiF[2][j];
+    double Sc[6];  // upper triangle of S - W Q^T
+    Sc[0] = A[3][3] - ((W[0][0] * A[3][0] + W[0][1] * A[3][1]) + W[0][2] * A[3][2]);
+    Sc[1] = A[3][4] - ((W[0][0] * A[4][0] + W[0][1] * A[4][1]) + W[0][2] * A[4][2]);
+    Sc[2] = A[3][5] - ((W[0][0] * A[5][0] + W[0][1] * A[5][1]) + W[0][2] * A[5][2]);
+    Sc[3] = A[4][4] - ((W[1][0] * A[4][0] + W[1][1] * A[4][1]) + W[1][2] * A[4][2]);
+    Sc[4] = A[4][5] - ((W[1][0] * A[5][0] + W[1][1] * A[5][1]) + W[1][2] * A[5][2]);
+    Sc[5] = A[5][5] - ((W[2][0] * A[5][0] + W[2][1] * A[5][1]) + W[2][2] * A[5][2]);
+    double Si[6];
+    if (inv3_sym_dev(Sc, Si) != 0) return -1;
+    double r2[3];
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-        double dj = A[j][j];
+    for (int i = 0; i < 3; i++) r2[i] = b[3 + i] - ((W[i][0] * b[0] + W[i][1] * b[1]) + W[i][2] * b[2]);
+    x[3] = (Si[0] * r2[0] + Si[1] * r2[1]) + Si[2] * r2[2];
+    x[4] = (Si[1] * r2[0] + Si[3] * r2[1]) + Si[4] * r2[2];
+    x[5] = (Si[2] * r2[0] + Si[4] * r2[1]) + Si[5] * r2[2];
+    double r1[3];  // b1 - Q^T x2
 #pragma unroll
-        for (int k = 0; k < j; k++) dj = dj - (L[j][k] * L[j][k]) * d[k];
-        bad = bad || !(dj > 0.0) || isinf(dj);
-        d[j] = dj;
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
-            double v = A[i][j];
-#pragma unroll
-            for (int k = 0; k < j; k++) v = v - (L[i][k] * L[j][k]) * d[k];
-            L[i][j] = v / dj;
-        }
-    }
-    if (bad) return -1;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double v = b[i];
-#pragma unroll
-        for (int k = 0; k < i; k++) v = v - L[i][k] * y[k];
-        y[i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; i++) y[i] = y[i] / d[i];
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-        double v = y[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; k++) v = v - L[k][i] * x[k];
-        x[i] = v;
-    }
+    for (int k = 0; k < 3; k++) r1[k] = b[k] - ((A[3][k] * x[3] + A[4][k] * x[4]) + A[5][k] * x[5]);
+    x[0] = (PiF[0][0] * r1[0] + PiF[0][1] * r1[1]) + PiF[0][2] * r1[2];
+    x[1] = (PiF[1][0] * r1[0] + PiF[1][1] * r1[1]) + PiF[1][2] * r1[2];
+    x[2] = (PiF[2][0] * r1[0] + PiF[2][1] * r1[1]) + PiF[2][2] * r1[2];
 #pragma unroll
     for (int i = 0; i < 6; i++)
         if (isnan(x[i]) || isinf(x[i])) return -1;
@@ -93,20 +103,40 @@ struct IcpLocal {
     long long tdbg[3];
 };
 
-// end-of-pass logic (ONE thread per CTA): convergence test, 6x6 solve, Euler-ZYX update, T <- U T.
-// ~6,000 cycles per pass.  It is a latency chain (six pivots, each behind an fp64 division, then two substitutions and
-// the sin/cos polynomials), not an instruction-count problem: a warp-parallel version (row i of the factorisation on
-// lane i, the three sin/cos pairs on three lanes, U T on twelve) was measured at 7,400 cycles and dropped.
-// fA / fb: the normal equations A x = b already converted to fp64 (shared memory, filled by 27 threads)
-__device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, const double (*fA)[6], const double *fb,
-                                             double isc_d, double rel_fit, double rel_rmse, int max_iter, int ns) {
+// End-of-pass logic, run redundantly by every CTA on the same 29 integer sums.  It is a latency chain on the fp64 pipe
+// (PCR_ICP_TRACE, cycles per pass at 100k points, round 1: an unpivoted LDL^T 3,936 — six pivots each behind an fp64
+// division, 21 divisions in all —, the three sin/cos 930, compose 304, statistics ~700), not an instruction-count problem.
+// The solve is now the block form above (rule D8), and the INDEPENDENT pieces
+// run on different warps of the CTA instead of one after the other on one thread (round 2; same arithmetic, same bits):
+//   step 1   warp 0: 6x6 solve -> x              ||  warp 1: fitness, RMSE, convergence / iteration-limit decision
+//   step 2   warps 0, 1, 2: sin/cos of x[0], x[1], x[2]
+//   step 3   thread 0: Euler-ZYX update U, T <- U T, bookkeeping
+// A warp-parallel LDL^T (row i on lane i, shuffles) was measured slower than the serial one (7,400 vs 6,000 cycles).
+struct IcpEnd {
+    double x[6], sn[3], cs[3];
+    int solved, stop;
+};
+
+// step 1a (one thread): x = solve(A, b); solved = 0 when there is no correspondence or the factorisation fails
+__device__ __noinline__ void icp_end_solve(IcpEnd *E, const long long *acc, const double (*fA)[6], const double *fb) {
+    int ok = 0;
+    if (acc[27] > 0) {
+        double x[6];
+        if (solve6_block_dev(fA, fb, x) == 0) {
+            ok = 1;
+#pragma unroll
+            for (int i = 0; i < 6; i++) E->x[i] = x[i];
+        }
+    }
+    E->solved = ok;
+}
+
+// step 1b (one thread): statistics of the pass that just ended and the stop decision
+__device__ __forceinline__ void icp_end_stats(IcpLocal *L, IcpEnd *E, const long long *acc, double isc_d, double rel_fit, double rel_rmse,
+                                              int max_iter, int ns) {
     const long long cnt = acc[27], sumq = acc[28];
     const double fit = (double)cnt / (double)ns;
     const double rmse = cnt > 0 ? sqrt(((double)sumq * isc_d) / (double)cnt) : 0.0;
-    L->fitness = fit;
-    L->rmse = rmse;
-    L->count = cnt;
-    L->sumq = sumq;
     const int pass = L->pass;
     bool stop = false;
     if (pass > 0 && fabs(L->prev_fit - fit) < rel_fit && fabs(L->prev_rmse - rmse) < rel_rmse) {
@@ -114,29 +144,31 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
         stop = true;
     }
     if (!stop && pass >= max_iter) stop = true;
-    if (stop) {
-        L->done = 1;
-    } else {
+    L->fitness = fit;
+    L->rmse = rmse;
+    L->count = cnt;
+    L->sumq = sumq;
+    if (!stop) {
         L->prev_fit = fit;
         L->prev_rmse = rmse;
+    }
+    E->stop = stop ? 1 : 0;
+}
+
+// step 3 (one thread): T <- U T
+__device__ __forceinline__ void icp_end_compose(IcpLocal *L, const IcpEnd *E) {
+    const int pass = L->pass;
+    if (E->stop) {
+        L->done = 1;
+    } else {
         double U[16];
         for (int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
-        const long long t0 = clock64();
-        long long t1 = t0, t2 = t0;
-        if (cnt > 0) {
-            double x[6];
-            const int rc = ldlt6_solve_dev(fA, fb, x);
-            t1 = clock64();
-            if (rc == 0) {
-                double sa, ca, sb, cb, sg, cg;
-                pcr_sincos(x[0], &sa, &ca);
-                pcr_sincos(x[1], &sb, &cb);
-                pcr_sincos(x[2], &sg, &cg);
-                U[0] = cb * cg;  U[1] = (sa * sb) * cg - ca * sg;  U[2] = (ca * sb) * cg + sa * sg;  U[3] = x[3];
-                U[4] = cb * sg;  U[5] = (sa * sb) * sg + ca * cg;  U[6] = (ca * sb) * sg - sa * cg;  U[7] = x[4];
-                U[8] = -sb;      U[9] = sa * cb;                   U[10] = ca * cb;                  U[11] = x[5];
-            }
-            t2 = clock64();
+        if (E->solved) {
+            const double sa = E->sn[0], ca = E->cs[0], sb = E->sn[1], cb = E->cs[1], sg = E->sn[2], cg = E->cs[2];
+            const double *x = E->x;
+            U[0] = cb * cg;  U[1] = (sa * sb) * cg - ca * sg;  U[2] = (ca * sb) * cg + sa * sg;  U[3] = x[3];
+            U[4] = cb * sg;  U[5] = (sa * sb) * sg + ca * cg;  U[6] = (ca * sb) * sg - sa * cg;  U[7] = x[4];
+            U[8] = -sb;      U[9] = sa * cb;                   U[10] = ca * cb;                  U[11] = x[5];
         }
         double Tn[16];
         for (int i = 0; i < 3; i++)
@@ -149,7 +181,6 @@ __device__ __noinline__ void icp_finish_pass(IcpLocal *L, const long long *acc, 
         Tn[15] = 1.0;
         for (int i = 0; i < 16; i++) L->T[i] = Tn[i];
         L->iterations = pass + 1;
-        L->tdbg[0] = t1 - t0; L->tdbg[1] = t2 - t1; L->tdbg[2] = clock64() - t2;
     }
     L->pass = pass + 1;
 }
@@ -328,6 +359,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
     __shared__ long long tot[29];
     __shared__ double fA[6][6], fb[6];
     __shared__ IcpLocal L;
+    __shared__ IcpEnd E;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 16) L.T[threadIdx.x] = S->T[threadIdx.x];
     if (threadIdx.x == 0) {
@@ -472,7 +504,17 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 29) S->acc3[(pass + 2) % 3][threadIdx.x - 32] = 0;
         __syncthreads();
         const long long c2 = clock64();
-        if (threadIdx.x == 0) icp_finish_pass(&L, tot, fA, fb, isc_d, rel_fit, rel_rmse, max_iter, ns);
+        if (threadIdx.x == 0) icp_end_solve(&E, tot, fA, fb);
+        else if (threadIdx.x == 32) icp_end_stats(&L, &E, tot, isc_d, rel_fit, rel_rmse, max_iter, ns);
+        __syncthreads();
+        const long long c3 = clock64();
+        if (!E.stop && E.solved && lane == 0 && warp < 3) pcr_sincos(E.x[warp], &E.sn[warp], &E.cs[warp]);
+        __syncthreads();
+        const long long c4 = clock64();
+        if (threadIdx.x == 0) {
+            icp_end_compose(&L, &E);
+            L.tdbg[0] = c3 - c2; L.tdbg[1] = c4 - c3; L.tdbg[2] = clock64() - c4;
+        }
         __syncthreads();
         if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgfin[pass], (unsigned long long)(clock64() - c2));
         if (trace && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -632,7 +674,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
             fprintf(stderr, "\n[pcr icp] slowest CTA finish per pass:");
             for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgfin[i]);
             fprintf(stderr, "  barrier alone %.0f\n", (double)hS->dbg[3] / hS->pass);
-            fprintf(stderr, "[pcr icp] end-of-pass logic of CTA 0, cycles per pass: LDL^T %.0f  sin/cos + update %.0f  compose %.0f\n",
+            fprintf(stderr, "[pcr icp] end-of-pass logic of CTA 0, cycles per pass: solve || statistics %.0f  sin/cos %.0f  compose %.0f\n",
                     (double)hS->dbg2[0] / hS->pass, (double)hS->dbg2[1] / hS->pass, (double)hS->dbg2[2] / hS->pass);
         }
         // passes that did work (the rest returned at the `done` check): iterations + 1

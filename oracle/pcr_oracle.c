@@ -33,6 +33,7 @@
  *   D6 RANSAC sampling: Philox4x32-10 keyed by seed, counter = global hypothesis index; result is
  *      that of the sequential (single-thread) Open3D loop.
  *   D7 ICP transforms the ORIGINAL fp32 source by the cumulative fp64 transform each pass.
+ *   D8 (part) the 6x6 point-to-plane system is solved by block elimination with closed-form 3x3 inverses (solve6_block).
  *
  * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off).
  */
@@ -1024,32 +1025,53 @@ typedef struct {
     int converged;
 } orc_icp_result;
 
-/* LDL^T without pivoting; returns 0 on success.  A: 6x6 symmetric full, b: rhs, x: solution */
-static int ldlt6_solve(const double A[6][6], const double *b, double *x) {
-    double L[6][6], d[6], y[6];
-    memset(L, 0, sizeof(L));
-    for (int j = 0; j < 6; j++) {
-        double dj = A[j][j];
-        for (int k = 0; k < j; k++) dj -= (L[j][k] * L[j][k]) * d[k];
-        if (!(dj > 0.0) || dj == INFINITY) return -1;
-        d[j] = dj;
-        for (int i = j + 1; i < 6; i++) {
-            double v = A[i][j];
-            for (int k = 0; k < j; k++) v -= (L[i][k] * L[j][k]) * d[k];
-            L[i][j] = v / dj;
-        }
-    }
-    for (int i = 0; i < 6; i++) {
-        double v = b[i];
-        for (int k = 0; k < i; k++) v -= L[i][k] * y[k];
-        y[i] = v;
-    }
-    for (int i = 0; i < 6; i++) y[i] = y[i] / d[i];
-    for (int i = 5; i >= 0; i--) {
-        double v = y[i];
-        for (int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
-        x[i] = v;
-    }
+/* 6x6 SPD solve, rule D8 (round 2): block elimination over the rotation / translation 3x3 blocks with closed-form
+ * symmetric 3x3 inverses (adjugate over determinant), every operation written out and individually rounded:
+ *     A = [P Q^T; Q S],  Pi = P^-1,  W = Q Pi,  Sc = S - W Q^T,  x2 = Sc^-1 (b2 - W b1),  x1 = Pi (b1 - Q^T x2).
+ * It replaces the unpivoted LDL^T of round 1: on the device that was a chain of six pivots, each behind an fp64
+ * division (21 divisions, ~3,900 cycles per ICP pass on one thread while every SM waits); this form has TWO divisions
+ * on its critical path and wide instruction-level parallelism.  Open3D itself calls Eigen's pivoted LDL^T
+ * (oracle/pcr_oracle_literal.c does); tests/test_oracle_literal.py bounds the difference (final transform ~1e-9 against
+ * the 1e-5 tolerance).  Returns 0 on success, -1 when a block is not positive (det <= 0) or the result is not finite. */
+static int inv3_sym(const double m[6] /* 00 01 02 11 12 22 */, double o[6]) {
+    const double c00 = m[3] * m[5] - m[4] * m[4];
+    const double c01 = m[2] * m[4] - m[1] * m[5];
+    const double c02 = m[1] * m[4] - m[2] * m[3];
+    const double det = (m[0] * c00 + m[1] * c01) + m[2] * c02;
+    if (!(det > 0.0) || det == INFINITY) return -1;
+    const double c11 = m[0] * m[5] - m[2] * m[2];
+    const double c12 = m[1] * m[2] - m[0] * m[4];
+    const double c22 = m[0] * m[3] - m[1] * m[1];
+    const double id = 1.0 / det;
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id; o[3] = c11 * id; o[4] = c12 * id; o[5] = c22 * id;
+    return 0;
+}
+
+static int solve6_block(const double A[6][6], const double *b, double *x) {
+    const double P[6] = {A[0][0], A[0][1], A[0][2], A[1][1], A[1][2], A[2][2]};
+    double Pi[6];
+    if (inv3_sym(P, Pi) != 0) return -1;
+    const double PiF[3][3] = {{Pi[0], Pi[1], Pi[2]}, {Pi[1], Pi[3], Pi[4]}, {Pi[2], Pi[4], Pi[5]}};
+    double W[3][3]; /* W = Q Pi, Q[i][k] = A[3 + i][k] */
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) W[i][j] = (A[3 + i][0] * PiF[0][j] + A[3 + i][1] * PiF[1][j]) + A[3 + i][2] * PiF[2][j];
+    double Sc[6]; /* upper triangle of S - W Q^T */
+    int e = 0;
+    for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++)
+            Sc[e++] = A[3 + i][3 + j] - ((W[i][0] * A[3 + j][0] + W[i][1] * A[3 + j][1]) + W[i][2] * A[3 + j][2]);
+    double Si[6];
+    if (inv3_sym(Sc, Si) != 0) return -1;
+    double r2[3];
+    for (int i = 0; i < 3; i++) r2[i] = b[3 + i] - ((W[i][0] * b[0] + W[i][1] * b[1]) + W[i][2] * b[2]);
+    x[3] = (Si[0] * r2[0] + Si[1] * r2[1]) + Si[2] * r2[2];
+    x[4] = (Si[1] * r2[0] + Si[3] * r2[1]) + Si[4] * r2[2];
+    x[5] = (Si[2] * r2[0] + Si[4] * r2[1]) + Si[5] * r2[2];
+    double r1[3]; /* b1 - Q^T x2 */
+    for (int k = 0; k < 3; k++) r1[k] = b[k] - ((A[3][k] * x[3] + A[4][k] * x[4]) + A[5][k] * x[5]);
+    x[0] = (PiF[0][0] * r1[0] + PiF[0][1] * r1[1]) + PiF[0][2] * r1[2];
+    x[1] = (PiF[1][0] * r1[0] + PiF[1][1] * r1[1]) + PiF[1][2] * r1[2];
+    x[2] = (PiF[2][0] * r1[0] + PiF[2][1] * r1[1]) + PiF[2][2] * r1[2];
     for (int i = 0; i < 6; i++) if (!(x[i] == x[i]) || x[i] == INFINITY || x[i] == -INFINITY) return -1;
     return 0;
 }
@@ -1168,7 +1190,7 @@ ORC_API int orc_icp_point_to_plane(const float *src, int ns, const float *tgt, c
             for (int a = 0; a < 6; a++)
                 for (int c = a; c < 6; c++) { Am[a][c] = Am[c][a] = ldexp((double)S.JJ[e], -2 * s_J); e++; }
             for (int a = 0; a < 6; a++) bv[a] = -ldexp((double)S.Jr[a], -(s_J + s_R));
-            if (ldlt6_solve(Am, bv, x) == 0) vec6_to_mat4(x, U);
+            if (solve6_block(Am, bv, x) == 0) vec6_to_mat4(x, U);
         }
         double Tn[16];
         mat4_mul_affine(U, T, Tn);
