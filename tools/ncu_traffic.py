@@ -26,7 +26,7 @@ def dram(r):
         t += float(r[col[n]].replace(",", "")) * mul.get(units[col[n]], 1.0)
     return t
 cls = {"k_ransac_validate": "ransac_validate", "k_knn_cov": "knn_cov", "k_icp_persist": "icp_pass", "k_fpfh": "fpfh",
-       "k_match_tc": "nn_features", "k_match_final": "match_misc", "k_celllists_build": "celllists_build", "k_knn_list": "knn_list",
+       "k_match_tc": "nn_features", "k_match_final": "match_misc", "k_celllists_": "celllists_build", "k_knn_list": "knn_list",
        "k_ransac_generate": "ransac_generate", "k_spfh": "spfh"}
 acc = {}
 for r in rows[2:]:

@@ -8,7 +8,7 @@ from pcr_b200.engine import Engine
 eng = Engine(0)
 v = 0.005
 src, tgt, _ = synth.make_pair(100000, v, 20242)
-p = eng.default_params(v); p.ransac_max_iter = 20000; p.ransac_confidence = 1.0; p.seed = 7; p.icp_max_iter = 4; p.icp_rel_fitness = 0.0; p.icp_rel_rmse = 0.0
+p = eng.default_params(v); p.ransac_max_iter = 100000; p.ransac_confidence = 1.0; p.seed = 7; p.icp_max_iter = 4; p.icp_rel_fitness = 0.0; p.icp_rel_rmse = 0.0
 for _ in range(2):
     r = eng.align_host(src, tgt, p)
 print("align ok", r.icp.fitness)
