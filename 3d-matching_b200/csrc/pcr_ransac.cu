@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     __shared__ double sT[12];
     __shared__ long long red[VAL_THREADS / 32][3];
     __shared__ long long s_best[2];
+    __shared__ long long s_tot;
     __shared__ unsigned int s_next;
     const unsigned int ns = *n_surv;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,12 +322,16 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
             const long long w = warp_sum_ll(q_add);
             if (lane == 0) red[warp][0] = w;
             found += __syncthreads_count(hit);
-            long long tot = 0;
-#pragma unroll
-            for (int k = 0; k < VAL_THREADS / 32; k++) tot += red[k][0];
-            partial += tot;
+            // the block total of this chunk: ONE warp adds the warp partials (every thread adding all of them was 8 % of the
+            // kernel's instructions); everybody picks it up after the barrier that the round needs anyway
+            if (warp == 0) {
+                long long v = lane < VAL_THREADS / 32 ? red[lane][0] : 0;
+                v = warp_sum_ll(v);
+                if (lane == 0) s_tot = v;
+            }
             const long long e_cnt = s_best[0], e_sumq = s_best[1];
-            __syncthreads();  // red / s_best are rewritten in the next round
+            __syncthreads();  // s_tot is visible; red / s_best are rewritten in the next round
+            partial += s_tot;
             const long long reachable = (long long)found + (ms - done_pts);
             if (reachable < e_cnt || (e_cnt > 0 && reachable == e_cnt && partial >= e_sumq)) {
                 pruned = true;
