@@ -46,6 +46,7 @@ struct Grid {
     int nx, ny, nz;
     int n;
     int R;                  // rings of cells that cover the search radius (1 unless built by pcr_grid_build_rings)
+    int big;                // the `start` table does not fit L2 comfortably: searches prefetch the rows of their block
 };
 
 
@@ -243,12 +244,42 @@ __device__ __forceinline__ int grid_cell(double v, double o, double inv_h, int n
     return (int)c;
 }
 
+// L2 prefetch of the cache line that holds *p (no register, no dependency): the searches below issue it for the `start`
+// entries of all nine rows of the 3x3x3 block before they walk the first one, so that on a table larger than L2 (the
+// dense ICP grid at 1M points is 340 MB) the later rows cost an L2 round trip instead of a DRAM one.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+typedef unsigned long long pcr_u64k;
+
+// smallest (d2, index) key over the contiguous range [b, e) of the cell-sorted cloud, FOUR loads in flight per lane
+// (the search is a chain of dependent loads: one candidate per round trip was ~700 cycles each, profiles/r2_summary.md).
+// Indices past the end are clamped to the last point: examining a point twice cannot change a minimum.
+__device__ __forceinline__ pcr_u64k grid_scan_min(const float4 *__restrict__ sorted, uint32_t b, uint32_t e, float qx, float qy,
+                                                  float qz, pcr_u64k bkey) {
+#pragma unroll 1
+    for (uint32_t k = b; k < e; k += 4) {
+        const uint32_t last = e - 1;
+        const float4 p0 = __ldg(sorted + k), p1 = __ldg(sorted + min(k + 1, last));
+        const float4 p2 = __ldg(sorted + min(k + 2, last)), p3 = __ldg(sorted + min(k + 3, last));
+        const pcr_u64k k0 = (((pcr_u64k)__float_as_uint(dist2f(qx, qy, qz, p0.x, p0.y, p0.z))) << 32) | (uint32_t)__float_as_int(p0.w);
+        const pcr_u64k k1 = (((pcr_u64k)__float_as_uint(dist2f(qx, qy, qz, p1.x, p1.y, p1.z))) << 32) | (uint32_t)__float_as_int(p1.w);
+        const pcr_u64k k2 = (((pcr_u64k)__float_as_uint(dist2f(qx, qy, qz, p2.x, p2.y, p2.z))) << 32) | (uint32_t)__float_as_int(p2.w);
+        const pcr_u64k k3 = (((pcr_u64k)__float_as_uint(dist2f(qx, qy, qz, p3.x, p3.y, p3.z))) << 32) | (uint32_t)__float_as_int(p3.w);
+        const pcr_u64k ka = k0 < k1 ? k0 : k1, kb = k2 < k3 ? k2 : k3;
+        const pcr_u64k kc = ka < kb ? ka : kb;
+        bkey = kc < bkey ? kc : bkey;
+    }
+    return bkey;
+}
+
 // radius-limited 1-NN in a grid: best (d2, idx) under the (d2, idx) lexicographic order, d2 < r2 strictly.
 // Returns original index or -1.  `seed` (optional, an index into `tgt_orig`, e.g. the previous ICP pass's
 // correspondence) only tightens the initial bound: the result is identical with or without it, because every
 // cell that intersects the closed ball of the current best distance is still visited (rows by slab distance,
 // cells of a row by x distance; both bounds carry a 1e-4-cell slack that dominates the fp32 rounding involved,
-// and cells at exactly the best distance are kept since ties are decided by index).
+// and cells at exactly the best distance are kept since ties are decided by index).  Visiting MORE cells of the block
+// than necessary never changes the result, so the row ranges of a z-slab are fetched together (one round trip for up
+// to three rows) with the x window the bound allowed when the slab was entered.
 __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy, float qz, float r2, int seed,
                                                const float4 *__restrict__ tgt_orig, float *d2_out) {
     const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
@@ -257,7 +288,7 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
     const int cz = (int)fmin(fmax(floor(fz), -2.0), (double)g.nz + 1.0);
     // best (d2, idx) as ONE 64-bit key (fp32 bits of d2 >= 0 order like the value; index in the low word): the
     // lexicographic tie rule D2 becomes a branch-free unsigned compare.  Start key = (r2, 0): only d2 < r2 beats it.
-    typedef unsigned long long u64k;
+    typedef pcr_u64k u64k;
     const uint32_t r2bits = __float_as_uint(r2);
     u64k bkey = ((u64k)r2bits) << 32;
     if (seed >= 0) {
@@ -273,6 +304,10 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
         const float fxf = (float)fmin(fmax(fx, -4.0), (double)g.nx + 4.0);
         const float fyf = (float)fmin(fmax(fy, -4.0), (double)g.ny + 4.0), fzf = (float)fmin(fmax(fz, -4.0), (double)g.nz + 4.0);
         const float h2 = (float)(g.h * g.h), inv_hf = (float)g.inv_h;
+        if (g.big) {
+            for (int z = z0; z <= z1; z++)
+                for (int y = y0; y <= y1; y++) prefetch_l2(g.start + ((long long)z * g.ny + y) * g.nx + x0);
+        }
         // home row first: it usually holds the nearest point
         if (cy >= y0 && cy <= y1 && cz >= z0 && cz <= z1) {
             const float best = __uint_as_float((uint32_t)(bkey >> 32));
@@ -282,12 +317,7 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
                 const long long row = ((long long)cz * g.ny + cy) * g.nx;
                 const uint32_t b = __ldg(g.start + row + xa);
                 const uint32_t e = __ldg(g.start + row + xb + 1);
-                for (uint32_t k = b; k < e; k++) {
-                    const float4 p = __ldg(g.sorted + k);
-                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
-                    bkey = key < bkey ? key : bkey;
-                }
+                bkey = grid_scan_min(g.sorted, b, e, qx, qy, qz, bkey);
             }
         }
         // then only the rows inside the window that the current best distance reaches in y and z (typically 1-3 of the
@@ -297,28 +327,29 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
             const float rw = sqrtf(best0) * inv_hf * 1.0001f + 1e-4f;
             const int ya = max(y0, (int)floorf(fyf - rw)), yb = min(y1, (int)floorf(fyf + rw));
             const int za = max(z0, (int)floorf(fzf - rw)), zb = min(z1, (int)floorf(fzf + rw));
+            const int xa = max(x0, (int)floorf(fxf - rw)), xb = min(x1, (int)floorf(fxf + rw));
+            if (xa <= xb) {
 #pragma unroll 1
-            for (int z = za; z <= zb; z++) {
-#pragma unroll 1
-                for (int y = ya; y <= yb; y++) {
-                    if (y == cy && z == cz) continue;
-                    const float best = __uint_as_float((uint32_t)(bkey >> 32));
-                    const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
-                    const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
-                    const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
-                    if ((sy * sy + sz * sz) * h2 > best) continue;
-                    // cells of the row that can hold a point within the current best distance (in cell units, padded)
-                    const float rc = sqrtf(best) * inv_hf * 1.0001f + 1e-4f;
-                    const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
-                    if (xa > xb) continue;
-                    const long long row = ((long long)z * g.ny + y) * g.nx;
-                    const uint32_t b = __ldg(g.start + row + xa);
-                    const uint32_t e = __ldg(g.start + row + xb + 1);
-                    for (uint32_t k = b; k < e; k++) {
-                        const float4 p = __ldg(g.sorted + k);
-                        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                        const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
-                        bkey = key < bkey ? key : bkey;
+                for (int z = za; z <= zb; z++) {
+                    uint32_t rb[3], re[3];  // ya..yb is at most three rows (a subrange of y0..y1)
+#pragma unroll
+                    for (int o = 0; o < 3; o++) {
+                        const int y = ya + o;
+                        const bool ok = y <= yb && !(y == cy && z == cz);
+                        const long long row = ((long long)z * g.ny + (ok ? y : ya)) * g.nx;
+                        rb[o] = ok ? __ldg(g.start + row + xa) : 0u;
+                        re[o] = ok ? __ldg(g.start + row + xb + 1) : 0u;
+                    }
+#pragma unroll
+                    for (int o = 0; o < 3; o++) {
+                        if (rb[o] >= re[o]) continue;
+                        const int y = ya + o;
+                        const float best = __uint_as_float((uint32_t)(bkey >> 32));
+                        const float ey = fmaxf(fmaxf((float)y - fyf, fyf - (float)(y + 1)), 0.0f);
+                        const float ez = fmaxf(fmaxf((float)z - fzf, fzf - (float)(z + 1)), 0.0f);
+                        const float sy = fmaxf(ey - 1e-4f, 0.0f), sz = fmaxf(ez - 1e-4f, 0.0f);
+                        if ((sy * sy + sz * sz) * h2 > best) continue;
+                        bkey = grid_scan_min(g.sorted, rb[o], re[o], qx, qy, qz, bkey);
                     }
                 }
             }
@@ -330,8 +361,9 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
 }
 
 // Search variant that also returns a CERTIFICATE for later reuse.  It examines EVERY point of the 3x3x3 cell block
-// around the query (no pruning: the row ranges are fetched three rows per round trip), i.e. every target point within
-// one cell size h of the query, and keeps the two smallest keys (d2, index) and the third smallest d2:
+// around the query (no pruning: the row ranges are fetched three rows per round trip, the candidates four per round
+// trip), i.e. every target point within one cell size h of the query, and keeps the two smallest keys (d2, index) and
+// the third smallest d2:
 //   *d2_out   smallest examined d2 (+inf if the block is empty) — also when it is not below r2, so that a
 //             "no correspondence" result carries a certificate too;
 //   *other_lb lower bound of the squared distance from the query to every target point OTHER than the nearest
@@ -341,7 +373,7 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
 // The nearest neighbour itself is found exactly as by grid_nn1 (same key order, same radius rule).
 __device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, float qz, float r2, float *d2_out,
                                              float *other_lb, int *j2, float *third_lb) {
-    typedef unsigned long long u64k;
+    typedef pcr_u64k u64k;
     const double fx = ((double)qx - g.ox) * g.inv_h, fy = ((double)qy - g.oy) * g.inv_h, fz = ((double)qz - g.oz) * g.inv_h;
     const int cx = (int)fmin(fmax(floor(fx), -2.0), (double)g.nx + 1.0);
     const int cy = (int)fmin(fmax(floor(fy), -2.0), (double)g.ny + 1.0);
@@ -352,6 +384,10 @@ __device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, 
     float third = INFINITY;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     if (x0 <= x1) {
+        if (g.big) {
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); z++)
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); y++) prefetch_l2(g.start + ((long long)z * g.ny + y) * g.nx + x0);
+        }
 #pragma unroll 1
         for (int dz = -1; dz <= 1; dz++) {
             const int z = cz + dz;
@@ -367,14 +403,23 @@ __device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, 
             }
 #pragma unroll
             for (int o = 0; o < 3; o++) {
-                for (uint32_t k = rb[o]; k < re[o]; k++) {
-                    const float4 p = __ldg(g.sorted + k);
-                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    const u64k key = (((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p.w);
-                    const bool lt1 = key < k1, lt2 = key < k2;
-                    third = lt2 ? __uint_as_float((uint32_t)(k2 >> 32)) : fminf(third, d2);
-                    k2 = lt1 ? k1 : (lt2 ? key : k2);
-                    k1 = lt1 ? key : k1;
+#pragma unroll 1
+                for (uint32_t k = rb[o]; k < re[o]; k += 4) {
+                    const uint32_t last = re[o] - 1;
+                    float4 p[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) p[u] = __ldg(g.sorted + min(k + u, last));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        // a slot past the end examines nothing: key and distance +inf leave k1, k2 and third unchanged
+                        const bool live = k + u <= last;
+                        const float d2 = live ? dist2f(qx, qy, qz, p[u].x, p[u].y, p[u].z) : INFINITY;
+                        const u64k key = live ? ((((u64k)__float_as_uint(d2)) << 32) | (uint32_t)__float_as_int(p[u].w)) : ~0ull;
+                        const bool lt1 = key < k1, lt2 = key < k2;
+                        third = lt2 ? __uint_as_float((uint32_t)(k2 >> 32)) : fminf(third, d2);
+                        k2 = lt1 ? k1 : (lt2 ? key : k2);
+                        k1 = lt1 ? key : k1;
+                    }
                 }
             }
         }

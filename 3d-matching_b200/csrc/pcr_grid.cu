@@ -308,6 +308,7 @@ int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, 
     g->nx = gd.nx; g->ny = gd.ny; g->nz = gd.nz;
     g->n = n;
     g->R = 1;
+    g->big = (size_t)ncells * sizeof(uint32_t) > ((size_t)48 << 20) ? 1 : 0;
     while ((double)g->R * h < reach) g->R++;  // R h >= radius (1 + 2^-10): the block covers the radius with the margin
     return PCR_OK;
 }

@@ -31,11 +31,14 @@ struct IcpState {
     double isc_JJ, isc_Jr, isc_d;    // 2^-2(kq - e_J), 2^-((kq - e_J) + (kq - e_R)), 2^-k_d
     double T_out[16];
     int trace;             // PCR_ICP_TRACE=1: collect the cycle counters below (two extra atomics per CTA and pass)
+    long long dbgsearch[64];  // per-pass number of points that took the search path / the second tier (PCR_ICP_TRACE)
+    long long dbgtier2[64];
     long long dbgmax[64];  // per-pass slowest CTA loop
     long long dbgfin[64];  // per-pass slowest CTA finish
     long long dbgp[64];  // per-pass loop cycles of CTA 0 (first 64 passes)
     long long dbg2[4];   // PCR_ICP_TRACE: inside the end-of-pass logic of CTA 0 — LDL^T, sin/cos + update, compose
     long long dbg[4];  // clock cycles of CTA 0: point loop, reduction + barrier, end-of-pass logic (PCR_ICP_TRACE=1 prints them)
+    unsigned long long dbgcta[1024];  // PCR_ICP_TRACE: per CTA, loop cycles of pass 20 << 16 | SM id (copied back only with the trace on)
 };
 
 // 6x6 SPD solve, rule D8 (round 2; the same operations in the same order as oracle/pcr_oracle.c: solve6_block): block
@@ -155,34 +158,38 @@ __device__ __forceinline__ void icp_end_stats(IcpLocal *L, IcpEnd *E, const long
     E->stop = stop ? 1 : 0;
 }
 
-// step 3 (one thread): T <- U T
-__device__ __forceinline__ void icp_end_compose(IcpLocal *L, const IcpEnd *E) {
+// step 3 (warp 0): T <- U T, one entry of the new transform per lane (12 lanes; the same products and sums in the same
+// order as the serial form, so the same bits), then the bookkeeping on lane 0
+__device__ __forceinline__ void icp_end_compose(IcpLocal *L, const IcpEnd *E, int lane) {
     const int pass = L->pass;
-    if (E->stop) {
-        L->done = 1;
-    } else {
-        double U[16];
-        for (int i = 0; i < 16; i++) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    const bool upd = !E->stop;
+    double tn = 0.0;
+    if (upd && lane < 12) {
+        const int i = lane >> 2, j = lane & 3;
+        double u0 = i == 0 ? 1.0 : 0.0, u1 = i == 1 ? 1.0 : 0.0, u2 = i == 2 ? 1.0 : 0.0, u3 = 0.0;
         if (E->solved) {
+            // branch-free over the three rows (a - b c == a + (-b) c bit for bit; multiplying by +-1 is exact):
+            //   row 0: cb cg, (sa sb) cg - ca sg, (ca sb) cg + sa sg      row 1: cb sg, (sa sb) sg + ca cg, (ca sb) sg - sa cg
+            //   row 2: -sb, sa cb, ca cb
             const double sa = E->sn[0], ca = E->cs[0], sb = E->sn[1], cb = E->cs[1], sg = E->sn[2], cg = E->cs[2];
-            const double *x = E->x;
-            U[0] = cb * cg;  U[1] = (sa * sb) * cg - ca * sg;  U[2] = (ca * sb) * cg + sa * sg;  U[3] = x[3];
-            U[4] = cb * sg;  U[5] = (sa * sb) * sg + ca * cg;  U[6] = (ca * sb) * sg - sa * cg;  U[7] = x[4];
-            U[8] = -sb;      U[9] = sa * cb;                   U[10] = ca * cb;                  U[11] = x[5];
+            const double m = i == 0 ? cg : sg, n = i == 0 ? sg : cg, s1 = i == 0 ? -1.0 : 1.0;
+            const double r0 = cb * m, r1 = (sa * sb) * m + (s1 * ca) * n, r2 = (ca * sb) * m + (-s1 * sa) * n;
+            u0 = i == 2 ? -sb : r0;
+            u1 = i == 2 ? sa * cb : r1;
+            u2 = i == 2 ? ca * cb : r2;
+            u3 = E->x[3 + i];
         }
-        double Tn[16];
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 4; j++) {
-                double v = (U[4 * i] * L->T[j] + U[4 * i + 1] * L->T[4 + j]) + U[4 * i + 2] * L->T[8 + j];
-                if (j == 3) v = v + U[4 * i + 3];
-                Tn[4 * i + j] = v;
-            }
-        Tn[12] = Tn[13] = Tn[14] = 0.0;
-        Tn[15] = 1.0;
-        for (int i = 0; i < 16; i++) L->T[i] = Tn[i];
-        L->iterations = pass + 1;
+        double v = (u0 * L->T[j] + u1 * L->T[4 + j]) + u2 * L->T[8 + j];
+        if (j == 3) v = v + u3;
+        tn = v;
     }
-    L->pass = pass + 1;
+    __syncwarp();
+    if (upd && lane < 16) L->T[lane] = lane < 12 ? tn : (lane == 15 ? 1.0 : 0.0);
+    if (lane == 0) {
+        if (E->stop) L->done = 1;
+        else L->iterations = pass + 1;
+        L->pass = pass + 1;
+    }
 }
 
 #ifndef PCR_ICP_THREADS
@@ -190,10 +197,15 @@ __device__ __forceinline__ void icp_end_compose(IcpLocal *L, const IcpEnd *E) {
 #endif
 constexpr int ICP_THREADS = PCR_ICP_THREADS;  // a multiple of 128 (the accumulate phase works on groups of 4 warps x 128 rows)
 #ifndef PCR_ICP_CTAS
-#define PCR_ICP_CTAS (768 / PCR_ICP_THREADS)
+#define PCR_ICP_CTAS (1024 / PCR_ICP_THREADS)
 #endif
 constexpr int ICP_CTAS_PER_SM = PCR_ICP_CTAS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
+// first pass whose searches also produce certificates (plain pruned searches before it, certified reuse after it)
+#ifndef PCR_ICP_CERT_PASS
+#define PCR_ICP_CERT_PASS 2
+#endif
+constexpr int ICP_CERT_PASS = PCR_ICP_CERT_PASS;
 
 // Result of the correspondence step for one source point: target index (-1: none), fp32 squared distance, and the
 // matched target point and normal.
@@ -210,8 +222,8 @@ struct IcpMatch {
 //   st0[i] = (q_ref, w)   query position at the last certificate search (grid_nn1_cert, which examines every target
 //                         point within one cell size h > max_dist of q_ref) and the certificate w (below)
 //   st1[i] = (t_j, j)     current correspondence: target point and index (index -1: none)
-//   st2[i] = (n_j, -)     its normal
-//   cert2[i] = (j2, w3)   second tier (below)
+//   st2[i] = (n_j, w3)    its normal; w3 belongs to the second tier
+//   cert2[i] = (t_j2, j2) second tier (below): the second nearest point and its index
 //   w > 0 : a correspondence j exists; w is a lower bound of the squared distance from q_ref to every OTHER target
 //           point.  For the new position q, with delta = |q - q_ref|: every other point is at least sqrt(w) - delta
 //           away, so if dist(q, t_j) < sqrt(w) - delta then j is still the unique nearest point, and
@@ -221,17 +233,20 @@ struct IcpMatch {
 // Near-ties (second nearest almost as close as the nearest: a fraction ~1e-4 of the points, and persistently so once
 // the cloud has stopped moving — some even flip back and forth under the last-bit jitter of the converged transform)
 // would fail that test in every pass, and one such point stalls its whole CTA in a full search.  They take a second
-// tier: cert2[i] = (j2, w3) holds the second nearest point and a lower bound for every point other than the nearest
-// two; the winner of the exact (d2, index) key comparison between j and j2 is kept if it beats w3 as above.
+// tier: cert2[i] = (t_j2, j2) holds the second nearest point and st2[i].w = w3 a lower bound for every point other than
+// the nearest two; the winner of the exact (d2, index) key comparison between j and j2 is kept if it beats w3 as above.
 // Passes 0..1 use the cheaper pruned search while the cloud still moves (no certificate is read before pass 3).
 // All bound comparisons carry a 2e-5 relative slack on both sides, orders of magnitude above the fp32 rounding of
 // the distances involved, so a certified answer is always the exact answer.
 __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, const float4 *__restrict__ nrm, float3 q,
-                                             float r2, float max_dist_f, int pass, int i, float4 *__restrict__ st0,
-                                             float4 *__restrict__ st1, float4 *__restrict__ st2, float2 *__restrict__ cert2,
-                                             IcpMatch &o) {
-    if (pass >= 3) {
+                                             float r2, float max_dist_f, int pass, int i, IcpState *__restrict__ trc,
+                                             float4 *__restrict__ st0, float4 *__restrict__ st1, float4 *__restrict__ st2,
+                                             float4 *__restrict__ cert2, IcpMatch &o) {
+    if (pass > ICP_CERT_PASS) {
         const float4 c = st0[i], a = st1[i], b = st2[i];
+        // second tier: ONE coalesced 16-byte record (the second candidate's position and index; its bound w3 rides in
+        // st2.w) read on demand — it used to be (j2, w3) + a gather of tgt[j2], two chained misses for the 0.5 % of the
+        // points that take this tier in every steady pass
         const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
         const float delta = sqrtf((mx * mx + my * my) + mz * mz);
         if (c.w > 0.0f) {
@@ -245,25 +260,26 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
                 o.d2 = d1;
                 return;
             }
-            const float2 c2 = cert2[i];
-            const int j2 = __float_as_int(c2.x);
+            const float4 t2 = cert2[i];
+            if (trc && pass < 64) atomicAdd((unsigned long long *)&trc->dbgtier2[pass], 1ull);
+            const int j2 = __float_as_int(t2.w);
             if (j2 >= 0) {
                 typedef unsigned long long u64k;
-                const float4 t2 = __ldg(tgt + j2);
+                const float w3 = b.w;
                 const float d2b = dist2f(q.x, q.y, q.z, t2.x, t2.y, t2.z);
                 const u64k ka = (((u64k)__float_as_uint(d1)) << 32) | (uint32_t)j_old;
                 const u64k kb = (((u64k)__float_as_uint(d2b)) << 32) | (uint32_t)j2;
                 const bool a_wins = ka < kb;  // exactly the comparison the search makes between these two
                 const float dw = a_wins ? d1 : d2b;
-                if (dw < r2 && (sqrtf(dw) + delta) * 1.00002f < sqrtf(c2.y) * 0.99998f) {
+                if (dw < r2 && (sqrtf(dw) + delta) * 1.00002f < sqrtf(w3) * 0.99998f) {
                     if (!a_wins) {
                         // the pair swaps roles: w no longer bounds "all points but the nearest", so it is set to a
                         // value that always defers to this tier; w3 bounds every point outside the pair as before
                         const float4 n2 = __ldg(nrm + j2);
                         st0[i] = make_float4(c.x, c.y, c.z, 1.17549435e-38f);
                         st1[i] = make_float4(t2.x, t2.y, t2.z, __int_as_float(j2));
-                        st2[i] = n2;
-                        cert2[i] = make_float2(__int_as_float(j_old), c2.y);
+                        st2[i] = make_float4(n2.x, n2.y, n2.z, w3);
+                        cert2[i] = make_float4(a.x, a.y, a.z, __int_as_float(j_old));
                         o.tx = t2.x; o.ty = t2.y; o.tz = t2.z; o.nx = n2.x; o.ny = n2.y; o.nz = n2.z;
                     }
                     o.j = a_wins ? j_old : j2;
@@ -281,7 +297,8 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
     }
     float d2, other = 0.0f, third = 0.0f;
     int j, j2 = -1;
-    if (pass >= 2) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
+    if (trc && pass < 64) atomicAdd((unsigned long long *)&trc->dbgsearch[pass], 1ull);
+    if (pass >= ICP_CERT_PASS) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
     else j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
     o.j = j;
     o.d2 = d2;
@@ -289,15 +306,20 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
         const float4 tp = __ldg(tgt + j), np = __ldg(nrm + j);
         o.tx = tp.x; o.ty = tp.y; o.tz = tp.z; o.nx = np.x; o.ny = np.y; o.nz = np.z;
         st1[i] = make_float4(tp.x, tp.y, tp.z, __int_as_float(j));
-        if (pass >= 2) {
+        if (pass >= ICP_CERT_PASS) {
+            float4 t2 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+            if (j2 >= 0) {
+                t2 = __ldg(tgt + j2);
+                t2.w = __int_as_float(j2);
+            }
             st0[i] = make_float4(q.x, q.y, q.z, other);
-            st2[i] = np;
-            cert2[i] = make_float2(__int_as_float(j2), third);
+            st2[i] = make_float4(np.x, np.y, np.z, third);
+            cert2[i] = t2;
         }
     } else {
         st1[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
         // nothing inside the radius: every target point is at least min(nearest examined, h) away
-        if (pass >= 2) st0[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
+        if (pass >= ICP_CERT_PASS) st0[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
     }
 }
 
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
                                                                 const float4 *__restrict__ tgt, const float4 *__restrict__ nrm,
                                                                 float r2, IcpState *__restrict__ S, float4 *__restrict__ st0,
                                                                 float4 *__restrict__ st1, float4 *__restrict__ st2,
-                                                                float2 *__restrict__ cert2, int *__restrict__ corr) {
+                                                                float4 *__restrict__ cert2, int *__restrict__ corr) {
     __shared__ int rows[2][7][ICP_THREADS];
     __shared__ long long red[ICP_WARPS][9];
     __shared__ long long tot[29];
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
                 const float4 p = __ldg(src + i);
                 const float3 q = xform_pt(T, p.x, p.y, p.z);
                 IcpMatch m;
-                icp_point_nn(g, tgt, nrm, q, r2, max_dist_f, pass, i, st0, st1, st2, cert2, m);
+                icp_point_nn(g, tgt, nrm, q, r2, max_dist_f, pass, i, trace ? S : nullptr, st0, st1, st2, cert2, m);
                 if (m.j >= 0) {
                     // point-to-plane row in fp32, every operation individually rounded (as the oracle): J and r are
                     // quantised to kq <= 30 bits right here, so fp64 bought nothing but fp64-pipe time
@@ -443,17 +465,34 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         // CTA reduction, then one atomic per sum and CTA into the pass's accumulator
         long long *gacc = S->acc3[pass % 3];
         const long long c1 = clock64();
+        // Warp reduction of the eight 64-bit sums as a transposing butterfly: at offsets 16, 8, 4 a lane keeps half of its
+        // values and hands the other half to its partner (4 + 2 + 1 shuffles), then offsets 2 and 1 finish the one value
+        // left — 9 64-bit shuffles instead of 8 x 5, after which lane 4 m holds the warp total of value m.  The plain
+        // per-value reduction was 17 % of the kernel's instructions at 100k points, all warps of the SM hitting the
+        // 32-lane/clock shuffle pipe at the same moment at the end of every pass (profiles/r2_summary.md).
+        long long tv;
+        {
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            long long w4[4], w2[2];
 #pragma unroll
-        for (int e = 0; e < 7; e++) acc[e] = warp_sum_ll(acc[e]);
-        sumq = warp_sum_ll(sumq);
+            for (int k = 0; k < 4; k++) {
+                const long long lo = acc[k], hi = k + 4 < 7 ? acc[k + 4] : sumq;
+                w4[k] = (h16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h16 ? lo : hi, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) w2[k] = (h8 ? w4[k + 2] : w4[k]) + __shfl_xor_sync(0xffffffffu, h8 ? w4[k] : w4[k + 2], 8);
+            tv = (h4 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? w2[0] : w2[1], 4);
+            tv += __shfl_xor_sync(0xffffffffu, tv, 2);
+            tv += __shfl_xor_sync(0xffffffffu, tv, 1);
+        }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         __syncthreads();  // the accumulate phase of the last chunk is done in every warp before `red` is reused
-        if (lane == 0) {
-#pragma unroll
-            for (int e = 0; e < 7; e++) red[warp][e] = acc[e];
-            red[warp][7] = cnt;
-            red[warp][8] = sumq;
+        // value m = 4 [lane & 16] + 2 [lane & 8] + [lane & 4]: acc[0..6] in slots 0..6, the sum of d2 (value 7) in slot 8
+        if ((lane & 3) == 0) {
+            const int m = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            red[warp][m == 7 ? 8 : m] = tv;
         }
+        if (lane == 1) red[warp][7] = cnt;
         __syncthreads();
         if (threadIdx.x < 29) {
             // sum e lives in slot `sl` of the two warps of group `gr` (see the accumulate phase above)
@@ -484,6 +523,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         }
         const long long cb = clock64();
         if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgmax[pass], (unsigned long long)(c1 - c0));
+        if (trace && threadIdx.x == 0 && pass == 20 && blockIdx.x < 1024) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            S->dbgcta[blockIdx.x] = ((unsigned long long)(c1 - c0) << 16) | smid;
+        }
         icp_grid_barrier(&S->bar, (unsigned int)(pass + 1) * gridDim.x);
         const long long ce = clock64();
         if (threadIdx.x < 29) {
@@ -511,9 +555,9 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         if (!E.stop && E.solved && lane == 0 && warp < 3) pcr_sincos(E.x[warp], &E.sn[warp], &E.cs[warp]);
         __syncthreads();
         const long long c4 = clock64();
-        if (threadIdx.x == 0) {
-            icp_end_compose(&L, &E);
-            L.tdbg[0] = c3 - c2; L.tdbg[1] = c4 - c3; L.tdbg[2] = clock64() - c4;
+        if (warp == 0) {
+            icp_end_compose(&L, &E, lane);
+            if (lane == 0) { L.tdbg[0] = c3 - c2; L.tdbg[1] = c4 - c3; L.tdbg[2] = clock64() - c4; }
         }
         __syncthreads();
         if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgfin[pass], (unsigned long long)(clock64() - c2));
@@ -633,8 +677,9 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_ALLOC(st0, float4, (size_t)ns);
     PCR_ALLOC(st1, float4, (size_t)ns);
     PCR_ALLOC(st2, float4, (size_t)ns);
-    PCR_ALLOC(cert2, float2, (size_t)ns);
-    PCR_CUDA(cudaMemcpyAsync(dS, hS, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
+    PCR_ALLOC(cert2, float4, (size_t)ns);
+    const size_t state_bytes = hS->trace ? sizeof(IcpState) : offsetof(IcpState, dbgcta);
+    PCR_CUDA(cudaMemcpyAsync(dS, hS, state_bytes, cudaMemcpyHostToDevice, ctx->stream));
     float r2 = (float)(max_dist * max_dist);
     // cooperative launch: every CTA must be resident (the kernel synchronises the grid once per pass)
     int &occ = ctx->occ_icp;
@@ -652,7 +697,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
         PCR_LAUNCHED();
     }
     PCR_CUDA(cudaGetLastError());
-    PCR_CUDA(cudaMemcpyAsync(hS, dS, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(hS, dS, state_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (sync_result) {
         PCR_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < 16; i++) res->transformation[i] = hS->T_out[i];
@@ -671,9 +716,18 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
             for (int i = 0; i < hS->pass && i < 12; i++) fprintf(stderr, " %lld", hS->dbgp[i]);
             fprintf(stderr, "\n[pcr icp] slowest CTA loop per pass:");
             for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgmax[i]);
+            fprintf(stderr, "\n[pcr icp] points on the search path per pass:");
+            for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgsearch[i]);
+            fprintf(stderr, "\n[pcr icp] points on the second tier per pass:");
+            for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgtier2[i]);
             fprintf(stderr, "\n[pcr icp] slowest CTA finish per pass:");
             for (int i = 0; i < hS->pass && i < 24; i++) fprintf(stderr, " %lld", hS->dbgfin[i]);
             fprintf(stderr, "  barrier alone %.0f\n", (double)hS->dbg[3] / hS->pass);
+            if (hS->pass > 20) {
+                fprintf(stderr, "[pcr icp] pass 20, per CTA (index:sm:loop cycles):");
+                for (int i = 0; i < blocks && i < 1024; i++) fprintf(stderr, " %d:%llu:%llu", i, hS->dbgcta[i] & 0xffffull, hS->dbgcta[i] >> 16);
+                fprintf(stderr, "\n");
+            }
             fprintf(stderr, "[pcr icp] end-of-pass logic of CTA 0, cycles per pass: solve || statistics %.0f  sin/cos %.0f  compose %.0f\n",
                     (double)hS->dbg2[0] / hS->pass, (double)hS->dbg2[1] / hS->pass, (double)hS->dbg2[2] / hS->pass);
         }

@@ -258,6 +258,12 @@ def run_engine(args):
     ms_e2e, res_e = timed(lambda: eng.align_host(src_pin, tgt_pin, p_fixed), args.steps, args.warmup)
     ms_dev_np, _ = timed(lambda: eng.align_device(ds, dt, p_fixed), args.steps, 1)       # without profiling events
     ms_default, res_d = timed(lambda: eng.align_host(src_pin, tgt_pin, p_default), args.steps, 1)
+    # the same fixed-work step WITHOUT the full-resolution normals of the source, which Ply.__init__ estimates
+    # (src/ply/ply.py:65) but point-to-plane ICP never reads: reported beside the headline, not as the headline
+    p_lazy = params(True)
+    p_lazy.source_normals = 0
+    ms_lazy, res_l = timed(lambda: eng.align_host(src_pin, tgt_pin, p_lazy), args.steps, 1)
+    lazy_same = bool(np.array_equal(np.array(res_l.icp.transformation), np.array(res_e.icp.transformation)))
 
     # ---- roofline of the dominant kernel class -----------------------------------------------------------------------
     # dominant kernel class of the CRITICAL PATH: time a class spends on pcr_align's helper context (full-resolution
@@ -304,6 +310,7 @@ def run_engine(args):
 
     # ---- aux: RANSAC hypotheses/s (sharded over ranks) and ICP iterations/s at 1M points -------------------------------
     aux = {"align_ms_reference_default_criteria_e2e": ms_default,
+           "align_ms_e2e_without_unused_source_normals": ms_lazy, "without_source_normals_same_result": lazy_same,
            "align_ms_device_resident_no_profiling_events": ms_dev_np,
            "stage_ms_device": {k: float(v) for k, v in zip(
                ["preprocess_both_clouds", "_unused1", "_unused2", "match", "ransac",
