@@ -47,6 +47,14 @@ struct Grid {
     int n;
     int R;                  // rings of cells that cover the search radius (1 unless built by pcr_grid_build_rings)
     int big;                // the `start` table does not fit L2 comfortably: searches prefetch the rows of their block
+    // COMPACT form (pcr_grid_build_compact; blk != nullptr, start == nullptr): the dense `start` table of a fine grid over
+    // a surface is almost all empty cells (1M points in 437^3 cells: 340 MB, beyond L2, and its memset + scan dominated
+    // the ICP preparation).  Two levels instead: per block of 32 consecutive cell ids (an x-run) blk[b] = (number of
+    // OCCUPIED cells before the block, occupancy mask of the block), and cstart[r] = first sorted position of the r-th
+    // occupied cell (cstart[n_occ] = n).  start(c) = cstart[blk[c >> 5].x + popc(blk[c >> 5].y & lowbits(c & 31))]:
+    // 8 bytes per 32 cells + 4 bytes per occupied cell, one more dependent load than the dense table, all of it in L2.
+    const uint2 *blk;
+    const uint32_t *cstart;
 };
 
 
@@ -209,6 +217,9 @@ int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const 
 // Finer cells pay off for k-nearest queries on dense clouds, where the k-th neighbour is much closer than the radius.
 int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, int rings, const float *lo, const float *hi,
                          Grid *g);
+// same search structure in the COMPACT form (see Grid) when the dense table would be large, else the dense grid; only
+// for kernels that read the table through grid_start_at / grid_range (grid_nn1, grid_nn1_cert)
+int pcr_grid_build_compact(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo, const float *hi, Grid *g);
 // Morton-order copy of a cloud (dense counting sort on interleaved cell ids; .w = original index): consecutive
 // points are spatially compact, which the warp-cooperative joins rely on
 int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorted_out);
@@ -250,6 +261,27 @@ __device__ __forceinline__ int grid_cell(double v, double o, double inv_h, int n
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 typedef unsigned long long pcr_u64k;
+
+// number of points whose cell id is below c (0 <= c <= ncells): the dense table entry, or the two-level lookup
+__device__ __forceinline__ uint32_t grid_start_at(const Grid &g, long long c) {
+    if (!g.blk) return __ldg(g.start + c);
+    const uint2 b = __ldg(g.blk + (c >> 5));
+    return __ldg(g.cstart + (b.x + __popc(b.y & ((1u << (int)(c & 31)) - 1u))));
+}
+// [*b, *e) = sorted positions of the cells c0 .. c1 (inclusive, c0 <= c1 in one row); one block entry serves both ends when
+// they share a block
+__device__ __forceinline__ void grid_range(const Grid &g, long long c0, long long c1, uint32_t *b, uint32_t *e) {
+    if (!g.blk) {
+        *b = __ldg(g.start + c0);
+        *e = __ldg(g.start + c1 + 1);
+        return;
+    }
+    const long long c2 = c1 + 1;
+    const uint2 b0 = __ldg(g.blk + (c0 >> 5));
+    const uint2 b1 = (c2 >> 5) == (c0 >> 5) ? b0 : __ldg(g.blk + (c2 >> 5));
+    *b = __ldg(g.cstart + (b0.x + __popc(b0.y & ((1u << (int)(c0 & 31)) - 1u))));
+    *e = __ldg(g.cstart + (b1.x + __popc(b1.y & ((1u << (int)(c2 & 31)) - 1u))));
+}
 
 // smallest (d2, index) key over the contiguous range [b, e) of the cell-sorted cloud, FOUR loads in flight per lane
 // (the search is a chain of dependent loads: one candidate per round trip was ~700 cycles each, profiles/r2_summary.md).
@@ -315,8 +347,8 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
             const int xa = max(x0, (int)floorf(fxf - rc)), xb = min(x1, (int)floorf(fxf + rc));
             if (xa <= xb) {
                 const long long row = ((long long)cz * g.ny + cy) * g.nx;
-                const uint32_t b = __ldg(g.start + row + xa);
-                const uint32_t e = __ldg(g.start + row + xb + 1);
+                uint32_t b, e;
+                grid_range(g, row + xa, row + xb, &b, &e);
                 bkey = grid_scan_min(g.sorted, b, e, qx, qy, qz, bkey);
             }
         }
@@ -337,8 +369,8 @@ __device__ __forceinline__ int grid_nn1_seeded(const Grid &g, float qx, float qy
                         const int y = ya + o;
                         const bool ok = y <= yb && !(y == cy && z == cz);
                         const long long row = ((long long)z * g.ny + (ok ? y : ya)) * g.nx;
-                        rb[o] = ok ? __ldg(g.start + row + xa) : 0u;
-                        re[o] = ok ? __ldg(g.start + row + xb + 1) : 0u;
+                        rb[o] = re[o] = 0u;
+                        if (ok) grid_range(g, row + xa, row + xb, &rb[o], &re[o]);
                     }
 #pragma unroll
                     for (int o = 0; o < 3; o++) {
@@ -398,8 +430,8 @@ __device__ __forceinline__ int grid_nn1_cert(const Grid &g, float qx, float qy, 
                 const int y = cy + dy;
                 const bool ok = y >= 0 && y < g.ny;
                 const long long row = ((long long)z * g.ny + (ok ? y : 0)) * g.nx;
-                rb[dy + 1] = ok ? __ldg(g.start + row + x0) : 0u;
-                re[dy + 1] = ok ? __ldg(g.start + row + x1 + 1) : 0u;
+                rb[dy + 1] = re[dy + 1] = 0u;
+                if (ok) grid_range(g, row + x0, row + x1, &rb[dy + 1], &re[dy + 1]);
             }
 #pragma unroll
             for (int o = 0; o < 3; o++) {

@@ -309,7 +309,148 @@ int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, 
     g->n = n;
     g->R = 1;
     g->big = (size_t)ncells * sizeof(uint32_t) > ((size_t)48 << 20) ? 1 : 0;
+    g->blk = nullptr;
+    g->cstart = nullptr;
     while ((double)g->R * h < reach) g->R++;  // R h >= radius (1 + 2^-10): the block covers the radius with the margin
+    return PCR_OK;
+}
+
+// ---- compact grid (two-level table, see Grid) ----------------------------------------------------------------------
+// Same cells, same sorted order as the dense grid (ascending cell id; the order inside a cell is arbitrary there too), but
+// no per-cell table: a counting sort over BLOCKS of 32 consecutive cell ids, then every point ranks itself among the few
+// members of its block.  Tables: cnt/bstart[nblk + 1] and mask/popc[nblk + 1] (one allocation, one memset).
+__global__ void __launch_bounds__(256) k_cg_count(const float4 *__restrict__ pts, int n, GridDims g, uint32_t *__restrict__ cell,
+                                                  uint32_t *__restrict__ rank, uint32_t *__restrict__ cnt, uint32_t *__restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell_of(g, __ldg(pts + i));
+    cell[i] = c;
+    rank[i] = atomicAdd(cnt + (c >> 5), 1u);
+    atomicOr(mask + (c >> 5), 1u << (c & 31u));
+}
+
+// pc[b] = popc(mask[b]) (scanned in place afterwards: number of occupied cells before block b)
+__global__ void __launch_bounds__(256) k_cg_popc(const uint32_t *__restrict__ mask, long long nblk, uint32_t *__restrict__ pc) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk) pc[b] = __popc(mask[b]);
+}
+
+// block-ordered copies of (cell id, original index): slot = bstart[block] + arrival rank
+__global__ void __launch_bounds__(256) k_cg_scatter(int n, const uint32_t *__restrict__ cell, const uint32_t *__restrict__ rank,
+                                                    const uint32_t *__restrict__ bstart, uint2 *__restrict__ slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell[i];
+    slot[bstart[c >> 5] + rank[i]] = make_uint2(c, (uint32_t)i);
+}
+
+// every slot ranks itself among the members of its block by (cell id, slot); the first slot of a cell publishes the
+// cell's start; blk[b] = (occupied cells before b, mask) is written by the thread of the block's first slot, the entries
+// of empty blocks by k_cg_pack below
+__global__ void __launch_bounds__(256) k_cg_rank(const float4 *__restrict__ pts, int n, const uint2 *__restrict__ slot,
+                                                 const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ pc,
+                                                 const uint32_t *__restrict__ mask, float4 *__restrict__ sorted,
+                                                 uint32_t *__restrict__ cstart) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint2 me = slot[k];
+    const uint32_t b = me.x >> 5;
+    const uint32_t s0 = bstart[b], s1 = bstart[b + 1];
+    uint32_t below = 0, same_before = 0;
+    for (uint32_t m = s0; m < s1; m++) {
+        const uint32_t cm = slot[m].x;
+        below += cm < me.x;
+        same_before += (cm == me.x) & (m < (uint32_t)k);
+    }
+    float4 p = __ldg(pts + me.y);
+    p.w = __int_as_float((int)me.y);
+    sorted[s0 + below + same_before] = p;
+    if (same_before == 0) cstart[pc[b] + __popc(mask[b] & ((1u << (me.x & 31u)) - 1u))] = s0 + below;
+}
+
+__global__ void __launch_bounds__(256) k_cg_pack(const uint32_t *__restrict__ pc, const uint32_t *__restrict__ mask, long long nblk,
+                                                 uint2 *__restrict__ blk, uint32_t *__restrict__ cstart, int n) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nblk) blk[b] = make_uint2(pc[b], b < nblk ? mask[b] : 0u);  // entry nblk: (n_occ, 0), for c = ncells
+    if (b == 0) cstart[pc[nblk]] = (uint32_t)n;                            // sentinel after the last occupied cell
+}
+
+int pcr_grid_build_compact(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo_in, const float *hi_in, Grid *g) {
+    if (n <= 0 || !(radius > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: n=%d radius=%g", n, radius);
+    float lo[3], hi[3];
+    if (lo_in && hi_in) {
+        for (int d = 0; d < 3; d++) { lo[d] = lo_in[d]; hi[d] = hi_in[d]; }
+    } else {
+        PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));
+    }
+    for (int d = 0; d < 3; d++)
+        if (!(lo[d] <= hi[d]) || isinf(lo[d]) || isinf(hi[d]))
+            return pcr_fail(ctx, PCR_ERR_INVALID, "grid build: non-finite coordinates");
+    // small tables: the dense form is one dependent load shorter per lookup and its build is cheap
+    {
+        const double h0 = radius * (1.0 + 1.0 / 1024.0);
+        const double cells0 = (floor(((double)hi[0] - lo[0]) / h0) + 1) * (floor(((double)hi[1] - lo[1]) / h0) + 1) *
+                              (floor(((double)hi[2] - lo[2]) / h0) + 1);
+        const char *env = getenv("PCR_GRID_COMPACT");  // read per call: the tests compare the two forms in one process
+        const bool off = env && atoi(env) == 0;
+        if (off || cells0 <= (double)(1 << 22)) return pcr_grid_build_rings(ctx, pts, n, radius, 1, lo, hi, g);
+    }
+    const double reach = radius * (1.0 + 1.0 / 1024.0);
+    double h = reach;
+    long long nx, ny, nz;
+    for (;;) {  // cell ids are 32-bit and the block table takes a quarter byte per cell: up to 2^30 cells
+        nx = (long long)floor(((double)hi[0] - (double)lo[0]) / h) + 1;
+        ny = (long long)floor(((double)hi[1] - (double)lo[1]) / h) + 1;
+        nz = (long long)floor(((double)hi[2] - (double)lo[2]) / h) + 1;
+        if ((double)nx * (double)ny * (double)nz <= (double)(1LL << 30)) break;
+        h *= 1.25;
+    }
+    const long long ncells = nx * ny * nz;
+    const long long nblk = (ncells >> 5) + 1;  // blocks that hold a cell id 0 .. ncells (c = ncells is looked up as an end)
+    GridDims gd{(double)lo[0], (double)lo[1], (double)lo[2], 1.0 / h, (int)nx, (int)ny, (int)nz};
+    PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
+    uint32_t *rank = cell + n;
+    PCR_ALLOC(slot, uint2, (size_t)n);
+    PCR_ALLOC(sorted, float4, (size_t)n);
+    PCR_ALLOC(cstart, uint32_t, (size_t)n + 1);
+    PCR_ALLOC(blk, uint2, (size_t)nblk + 1);
+    KScope ks(ctx, KC_GRID_BUILD, 80.0 * n + 40.0 * (double)nblk, 7);
+    // [cnt -> bstart: nblk + 1][mask: nblk + 1][pc: nblk + 1][scan state x 2], one memset
+    const int tiles = div_up(nblk, 4096);
+    const size_t tab = (((size_t)nblk + 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t st_bytes = sizeof(unsigned long long) * ((size_t)tiles + 1);
+    unsigned char *base = arena<unsigned char>(ctx, 3 * tab + 2 * st_bytes);
+    if (!base) return PCR_ERR_OOM;
+    PCR_CUDA(cudaMemsetAsync(base, 0, 3 * tab + 2 * st_bytes, ctx->stream));
+    uint32_t *cnt = (uint32_t *)base, *mask = (uint32_t *)(base + tab), *pc = (uint32_t *)(base + 2 * tab);
+    unsigned long long *st_a = (unsigned long long *)(base + 3 * tab), *st_b = (unsigned long long *)(base + 3 * tab + st_bytes);
+    k_cg_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, rank, cnt, mask);
+    PCR_LAUNCHED();
+    k_scan_onepass<uint32_t><<<tiles, 1024, 0, ctx->stream>>>(cnt, nblk, st_a, (unsigned int *)(st_a + tiles));
+    PCR_LAUNCHED();
+    k_cg_popc<<<div_up(nblk, 256), 256, 0, ctx->stream>>>(mask, nblk, pc);
+    PCR_LAUNCHED();
+    k_scan_onepass<uint32_t><<<tiles, 1024, 0, ctx->stream>>>(pc, nblk, st_b, (unsigned int *)(st_b + tiles));
+    PCR_LAUNCHED();
+    k_cg_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(n, cell, rank, cnt, slot);
+    PCR_LAUNCHED();
+    k_cg_rank<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, slot, cnt, pc, mask, sorted, cstart);
+    PCR_LAUNCHED();
+    k_cg_pack<<<div_up(nblk + 1, 256), 256, 0, ctx->stream>>>(pc, mask, nblk, blk, cstart, n);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    g->sorted = sorted;
+    g->start = nullptr;
+    g->blk = blk;
+    g->cstart = cstart;
+    g->ox = gd.ox; g->oy = gd.oy; g->oz = gd.oz;
+    g->inv_h = gd.inv_h;
+    g->h = h;
+    g->nx = gd.nx; g->ny = gd.ny; g->nz = gd.nz;
+    g->n = n;
+    g->R = 1;
+    while ((double)g->R * h < reach) g->R++;
+    g->big = 0;
     return PCR_OK;
 }
 

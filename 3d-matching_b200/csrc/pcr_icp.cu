@@ -628,7 +628,7 @@ int pcr_icp_prepare(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, 
     PCR_TRY(pcr_bounds(ctx, tgt, nt, lo, hi));
     prep->amax = 0.0f;
     for (int d = 0; d < 3; d++) prep->amax = fmaxf(prep->amax, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
-    PCR_TRY(pcr_grid_build(ctx, tgt, nt, max_dist, lo, hi, &prep->g));
+    PCR_TRY(pcr_grid_build_compact(ctx, tgt, nt, max_dist, lo, hi, &prep->g));
     PCR_TRY(pcr_morton_sort(ctx, src, ns, &prep->src_sorted));
     prep->valid = true;
     return PCR_OK;
@@ -746,7 +746,7 @@ int pcr_nn1_impl(pcr_ctx *ctx, const float4 *tgt, int nt, const float4 *q, int n
         return PCR_OK;
     }
     Grid g;
-    PCR_TRY(pcr_grid_build(ctx, tgt, nt, radius, nullptr, nullptr, &g));
+    PCR_TRY(pcr_grid_build_compact(ctx, tgt, nt, radius, nullptr, nullptr, &g));
     KScope ks(ctx, KC_NN1, 16.0 * nt + 24.0 * nq);
     k_nn1<<<div_up(nq, 256), 256, 0, ctx->stream>>>(q, nq, g, (float)(radius * radius), idx, d2);
     PCR_LAUNCHED();

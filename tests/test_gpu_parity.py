@@ -450,3 +450,34 @@ def test_pipeline_matches_the_committed_golden(eng):
     assert np.array_equal(np.array(info.ransac.transformation).reshape(4, 4), g["ransac_T"])
     assert (info.n_src_down, info.n_tgt_down, info.n_corr) == (len(g["src_down"]), len(g["tgt_down"]), len(g["corr"]))
     assert info.icp.iterations == int(g["icp_iterations"])
+
+
+def test_compact_grid_equals_dense(orc, eng, pair, monkeypatch):
+    """The two-level (compact) search grid that ICP and nn1 use on fine grids returns what the dense table returns:
+    radius-limited nearest neighbours (index and fp32 d2 bits, also against the oracle) and a whole ICP run."""
+    v = pair["v"]
+    moved = orc.transform_points(pair["T"], pair["src"])
+    dm = eng.pack(moved)
+    n = eng.estimate_normals(pair["dt"], 2 * v, 30)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PCR_GRID_COMPACT", mode)
+        idx, d2 = eng.nn1(pair["dt"], dm, 0.4 * v)          # (extent / 0.4 v)^3 cells: far above the compact threshold
+        g, corr = eng.icp_point_to_plane(pair["ds"], pair["dt"], n, 0.4 * v, pair["T"], 8, 0.0, 0.0)
+        out[mode] = (idx.cpu().numpy(), d2.cpu().numpy(), corr.cpu().numpy(), np.asarray(g.transformation), g.sum_d2_fixed)
+    for a, b in zip(out["1"], out["0"]):
+        assert np.array_equal(a, b)
+    oi, od = orc.nn1(pair["tgt"], moved, 0.4 * v)
+    assert np.array_equal(out["1"][0], oi) and np.array_equal(out["1"][1], od)
+    # a cloud with many points per cell and whole empty blocks: two clusters far apart, fine radius
+    rng = np.random.default_rng(5)
+    tgt = np.concatenate([rng.normal(0, 0.01, (3000, 3)), rng.normal(0, 0.01, (3000, 3)) + 4.0]).astype(np.float32)
+    q = np.concatenate([tgt[::3] + rng.normal(0, 0.002, (2000, 3)).astype(np.float32), rng.uniform(-1, 5, (500, 3)).astype(np.float32)])
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PCR_GRID_COMPACT", mode)
+        idx, d2 = eng.nn1(eng.pack(tgt), eng.pack(q), 0.01)
+        res[mode] = (idx.cpu().numpy(), d2.cpu().numpy())
+    oi, od = orc.nn1(tgt, q, 0.01)
+    assert np.array_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
+    assert np.array_equal(res["1"][0], oi) and np.array_equal(res["1"][1], od)
