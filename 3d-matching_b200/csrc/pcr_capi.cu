@@ -294,6 +294,10 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
         pcr_arena_reset(h);
         h->bounds_cache.clear();
     }
+    // the boxes of the two full clouds: one launch, one synchronisation, shared with the helper context (round 1: four
+    // reductions, each with its own init kernel and host synchronisation)
+    PCR_TRY(pcr_bounds_pair(ctx, src, ns, tgt, nt));
+    if (overlap) h->bounds_cache = ctx->bounds_cache;
     // (Preprocessing the two clouds concurrently was measured and gains nothing: each of its kernels fills the GPU.)
     int rc = preprocess_cloud(ctx, src, ns, v, &sd, &ms, &sn, &sf);
     if (rc == PCR_OK) rc = preprocess_cloud(ctx, tgt, nt, v, &td, &mt, &tn, &tf);

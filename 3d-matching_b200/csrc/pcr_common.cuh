@@ -122,6 +122,7 @@ struct pcr_ctx {
     // bounding boxes already reduced during the current exported call, keyed by (pointer, n); cleared on entry
     struct BoundsEntry { const void *ptr; int n; float lo[3], hi[3]; };
     std::vector<BoundsEntry> bounds_cache;
+    unsigned int *bounds_ticket = nullptr;  // device word: completion ticket of k_bounds2 (zero between launches)
     // RANSAC session (pcr_ransac_session_begin/end): prepared work in buffers that outlive the per-call arena
     struct RansacSession {
         bool active = false;
@@ -210,6 +211,8 @@ int pcr_pow2ceil_exp(double x);  // smallest e with 2^e >= x
 
 // bounds: lo/hi (host) of a float4 cloud; one device reduction + one D2H sync
 int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]);
+// both boxes with ONE launch and ONE synchronisation, into the per-call cache (either cloud may already be cached)
+int pcr_bounds_pair(pcr_ctx *ctx, const float4 *pa, int na, const float4 *pb, int nb);
 // build a search grid supporting radius-`radius` queries with a 3x3x3 cell probe.
 // If bounds are already known pass them (have_bounds), else they are computed.
 int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo, const float *hi, Grid *g);

@@ -214,6 +214,7 @@ int pcr_destroy(pcr_ctx *ctx) {
         if (b) cudaFree(b);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (const KPending &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (ctx->bounds_ticket) cudaFree(ctx->bounds_ticket);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -4,74 +4,131 @@
 // HBM roofline: algorithmic bytes = 16 n (read) + 4 n (cell ids) + 16 n (sorted write) + 4 (ncells+1).
 #include "pcr_common.cuh"
 
-// order-preserving float <-> int mapping for atomicMin/Max
-__device__ __forceinline__ int f2ord(float f) {
-    const int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-static inline float ord2f_host(int i) {
-    const int j = i >= 0 ? i : i ^ 0x7fffffff;
-    float f;
-    memcpy(&f, &j, 4);
-    return f;
-}
-
-__global__ void k_bounds_init(int *b) {
-    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;       // min
-    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000;  // max
-}
-
-__global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, int n, int *__restrict__ b) {
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// Bounding boxes of one or two clouds in ONE launch with no initialisation pass: every block reduces its share to six
+// floats, the last block to finish (ticket) folds the per-block results of each cloud and re-arms the ticket.  (Round 1:
+// an init kernel + a reduction with six same-address atomics per warp, per cloud, and a host synchronisation for each
+// of the four clouds an alignment looks at.)
+__global__ void __launch_bounds__(256) k_bounds2(const float4 *__restrict__ pa, int na, int blocks_a, const float4 *__restrict__ pb,
+                                                 int nb, float *__restrict__ part, unsigned int *__restrict__ ticket,
+                                                 float *__restrict__ out) {
+    __shared__ float sm[8][6];
+    __shared__ bool last;
+    const bool second = (int)blockIdx.x >= blocks_a;
+    const float4 *__restrict__ pts = second ? pb : pa;
+    const int n = second ? nb : na;
+    const int blk = second ? blockIdx.x - blocks_a : blockIdx.x, nblk = second ? gridDim.x - blocks_a : blocks_a;
+    float v[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int i = blk * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
         const float4 p = __ldg(pts + i);
-        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
-        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
-        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+        v[0] = fminf(v[0], p.x); v[3] = fmaxf(v[3], p.x);
+        v[1] = fminf(v[1], p.y); v[4] = fmaxf(v[4], p.y);
+        v[2] = fminf(v[2], p.z); v[5] = fmaxf(v[5], p.z);
     }
+    auto fold = [&]() {  // CTA-wide min / max of v[] into thread 0
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
+        for (int d = 0; d < 6; d++)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t = __shfl_xor_sync(0xffffffffu, v[d], o);
+                v[d] = d < 3 ? fminf(v[d], t) : fmaxf(v[d], t);
+            }
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int d = 0; d < 6; d++) sm[threadIdx.x >> 5][d] = v[d];
+        __syncthreads();
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                float t = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x][d] : (d < 3 ? INFINITY : -INFINITY);
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const float u = __shfl_xor_sync(0xffffffffu, t, o);
+                    t = d < 3 ? fminf(t, u) : fmaxf(t, u);
+                }
+                v[d] = t;
+            }
         }
-    }
-    if ((threadIdx.x & 31) == 0) {
+        __syncthreads();
+    };
+    fold();
+    if (threadIdx.x == 0) {
 #pragma unroll
+        for (int d = 0; d < 6; d++) part[(size_t)blockIdx.x * 6 + d] = v[d];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int cloud = 0; cloud < 2; cloud++) {
+        const int b0 = cloud ? blocks_a : 0, b1 = cloud ? (int)gridDim.x : blocks_a;
+#pragma unroll
+        for (int d = 0; d < 6; d++) v[d] = d < 3 ? INFINITY : -INFINITY;
+        for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x)
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                const float t = __ldcg(part + (size_t)b * 6 + d);
+                v[d] = d < 3 ? fminf(v[d], t) : fmaxf(v[d], t);
+            }
+        fold();
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int d = 0; d < 6; d++) out[cloud * 6 + d] = v[d];
+    }
+    if (threadIdx.x == 0) *ticket = 0u;  // re-armed for the next launch on this context's stream
+}
+
+static bool bounds_cached(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]) {
+    for (const auto &e : ctx->bounds_cache)
+        if (e.ptr == (const void *)pts && e.n == n) {  // same buffer earlier in this call: no second reduction + sync
+            if (lo)
+                for (int d = 0; d < 3; d++) { lo[d] = e.lo[d]; hi[d] = e.hi[d]; }
+            return true;
+        }
+    return false;
+}
+
+// bounding boxes of two clouds (the second may be empty: nb = 0) with one launch and one host synchronisation; both go
+// into the context's per-call cache
+int pcr_bounds_pair(pcr_ctx *ctx, const float4 *pa, int na, const float4 *pb, int nb) {
+    const bool need_a = na > 0 && !bounds_cached(ctx, pa, na, nullptr, nullptr);
+    const bool need_b = nb > 0 && !bounds_cached(ctx, pb, nb, nullptr, nullptr);
+    if (!need_a && !need_b) return PCR_OK;
+    if (!need_a) { pa = pb; na = nb; pb = nullptr; nb = 0; }
+    else if (!need_b) { pb = nullptr; nb = 0; }
+    if (!ctx->bounds_ticket) {
+        PCR_CUDA(cudaMalloc(&ctx->bounds_ticket, sizeof(unsigned int)));
+        PCR_CUDA(cudaMemsetAsync(ctx->bounds_ticket, 0, sizeof(unsigned int), ctx->stream));
+    }
+    const int blocks_a = min(div_up(na, 256), ctx->sm_count * 4);
+    const int blocks_b = nb > 0 ? min(div_up(nb, 256), ctx->sm_count * 4) : 0;
+    PCR_ALLOC(part, float, (size_t)(blocks_a + blocks_b) * 6 + 12);
+    float *out = part + (size_t)(blocks_a + blocks_b) * 6;
+    {
+        KScope ks(ctx, KC_BOUNDS, 16.0 * ((double)na + (double)nb));
+        k_bounds2<<<blocks_a + blocks_b, 256, 0, ctx->stream>>>(pa, na, blocks_a, pb, nb, part, ctx->bounds_ticket, out);
+        PCR_LAUNCHED();
+    }
+    float *hb = (float *)ctx->pinned;
+    PCR_CUDA(cudaMemcpyAsync(hb, out, 12 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int cloud = 0; cloud < (nb > 0 ? 2 : 1); cloud++) {
+        pcr_ctx::BoundsEntry e;
+        e.ptr = cloud ? (const void *)pb : (const void *)pa;
+        e.n = cloud ? nb : na;
         for (int d = 0; d < 3; d++) {
-            atomicMin(b + d, f2ord(lo[d]));
-            atomicMax(b + 3 + d, f2ord(hi[d]));
+            e.lo[d] = hb[cloud * 6 + d];
+            e.hi[d] = hb[cloud * 6 + 3 + d];
         }
+        ctx->bounds_cache.push_back(e);
     }
+    return PCR_OK;
 }
 
 int pcr_bounds(pcr_ctx *ctx, const float4 *pts, int n, float lo[3], float hi[3]) {
-    for (const auto &e : ctx->bounds_cache)
-        if (e.ptr == (const void *)pts && e.n == n) {  // same buffer earlier in this call: no second reduction + sync
-            for (int d = 0; d < 3; d++) { lo[d] = e.lo[d]; hi[d] = e.hi[d]; }
-            return PCR_OK;
-        }
-    PCR_ALLOC(b, int, 8);
-    {
-    KScope ks(ctx, KC_BOUNDS, 16.0 * n);
-    k_bounds_init<<<1, 32, 0, ctx->stream>>>(b);
-    PCR_LAUNCHED();
-    const int blocks = min(div_up(n, 256), ctx->sm_count * 8);
-    k_bounds<<<blocks, 256, 0, ctx->stream>>>(pts, n, b);
-    PCR_LAUNCHED();
-    }
-    int *hb = (int *)ctx->pinned;
-    PCR_CUDA(cudaMemcpyAsync(hb, b, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    pcr_ctx::BoundsEntry e;
-    e.ptr = pts;
-    e.n = n;
-    for (int d = 0; d < 3; d++) {
-        lo[d] = e.lo[d] = ord2f_host(hb[d]);
-        hi[d] = e.hi[d] = ord2f_host(hb[3 + d]);
-    }
-    ctx->bounds_cache.push_back(e);
+    if (bounds_cached(ctx, pts, n, lo, hi)) return PCR_OK;
+    PCR_TRY(pcr_bounds_pair(ctx, pts, n, nullptr, 0));
+    if (!bounds_cached(ctx, pts, n, lo, hi)) return pcr_fail(ctx, PCR_ERR_INVALID, "bounds: empty cloud");
     return PCR_OK;
 }
 
