@@ -22,7 +22,7 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
                    int *corr, int *c_host);
 int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, const int *corr, int c,
                     double max_dist, double edge_sim, int64_t max_iter, double confidence, u64 seed,
-                    pcr_reg_result *res);
+                    pcr_reg_result *res, const RansacWork *prepared = nullptr);
 int pcr_ransac_prepare(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist,
                        RansacWork *w);
 int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, double max_dist);
@@ -332,13 +332,42 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
             return cudaStreamSynchronize(h->stream) == cudaSuccess ? PCR_OK : PCR_ERR_CUDA;
         });
     }
+    // The RANSAC search structures (target grid, Morton-ordered source, candidate lists: ~150 us of small kernels with no
+    // host synchronisation) depend only on the down-sampled clouds: they are built on an auxiliary stream NEXT TO the
+    // descriptor matching instead of between matching and RANSAC (timeline: tools/gpu_timeline.py).
+    RansacWork rwork;
+    bool rwork_ok = false;
+    cudaEvent_t rprep_done = nullptr;
+    if (overlap && ctx->aux_stream && ms > 0 && mt > 0) {
+        cudaEvent_t down_ready;
+        PCR_CUDA(cudaEventCreateWithFlags(&down_ready, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(down_ready, ctx->stream));
+        PCR_CUDA(cudaStreamWaitEvent(ctx->aux_stream, down_ready, 0));
+        PCR_CUDA(cudaEventDestroy(down_ready));
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = ctx->aux_stream;
+        const int rcp = pcr_ransac_prepare(ctx, sd, ms, td, mt, 1.5 * v, &rwork);
+        ctx->stream = keep;
+        if (rcp != PCR_OK) {
+            if (ready) cudaEventDestroy(ready);
+            return rcp;
+        }
+        PCR_CUDA(cudaEventCreateWithFlags(&rprep_done, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(rprep_done, ctx->aux_stream));
+        rwork_ok = true;
+    }
     // global_registration (src/matcher/ransac.py:41-59): mutual filter True, threshold 1.5 v
     int c = 0;
     int *corr = arena<int>(ctx, 2 * (size_t)ms);
     rc = corr ? pcr_match_impl(ctx, sf, ms, tf, mt, 1, 0.1, corr, &c) : PCR_ERR_OOM;
     tm.mark();
+    if (rprep_done) {
+        cudaStreamWaitEvent(ctx->stream, rprep_done, 0);
+        cudaEventDestroy(rprep_done);
+    }
     if (rc == PCR_OK)
-        rc = pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed, &res->ransac);
+        rc = pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed, &res->ransac,
+                             rwork_ok ? &rwork : nullptr);
     tm.mark();
     if (overlap) {
         const int rch = ctx->worker->wait();

@@ -144,6 +144,7 @@ struct pcr_ctx {
     bool owns_stream = false;
     void *dist = nullptr;              // multi-GPU state (pcr_dist.cu): NCCL communicator, exchange buffers, worker contexts
     cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
+    cudaStream_t aux_stream = nullptr; // second highest-priority stream: work pcr_align issues next to its critical path
 };
 
 // one persistent host thread executing one task at a time

@@ -159,6 +159,10 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
             cudaGetLastError();
             ctx->hp_stream = nullptr;
         }
+        if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_high) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->aux_stream = nullptr;
+        }
         ctx->helper = h;
         ctx->worker = new Worker();
     }
@@ -219,6 +223,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return PCR_OK;
 }
@@ -253,6 +258,24 @@ int pcr_kernel_stats(pcr_ctx *ctx, pcr_kernel_stat *out, int cap, int reset) {
     if (!ctx || !out || cap < KC_COUNT) return PCR_ERR_INVALID;
     cudaSetDevice(ctx->device);
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (getenv("PCR_TIMELINE") && !ctx->pending.empty()) {
+        // diagnostic: start offset and duration of every timed scope since the last call, both contexts, relative to the
+        // first scope of this context (there is no nsys in the image; this is the poor man's timeline)
+        if (ctx->helper) cudaStreamSynchronize(ctx->helper->stream);
+        const cudaEvent_t t0 = ctx->pending.front().a;
+        for (int which = 0; which < 2; which++) {
+            pcr_ctx *c = which ? ctx->helper : ctx;
+            if (!c) continue;
+            for (const KPending &p : c->pending) {
+                float off = 0.0f, dur = 0.0f;
+                if (cudaEventElapsedTime(&off, t0, p.a) == cudaSuccess && cudaEventElapsedTime(&dur, p.a, p.b) == cudaSuccess)
+                    fprintf(stderr, "[pcr timeline] %s %-16s start %8.1f us  dur %7.1f us  (%lld launches)\n", which ? "helper" : "main  ",
+                            KNAMES[p.id], off * 1e3, dur * 1e3, p.launches);
+                else
+                    cudaGetLastError();
+            }
+        }
+    }
     for (const KPending &p : ctx->pending) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {

@@ -2,7 +2,11 @@
 // Replaces the KD-tree builds inside every Open3D call of the reference (KDTreeFlann).
 //
 // HBM roofline: algorithmic bytes = 16 n (read) + 4 n (cell ids) + 16 n (sorted write) + 4 (ncells+1).
+#include <cooperative_groups.h>
+
 #include "pcr_common.cuh"
+
+namespace cg = cooperative_groups;
 
 // Bounding boxes of one or two clouds in ONE launch with no initialisation pass: every block reduces its share to six
 // floats, the last block to finish (ticket) folds the per-block results of each cloud and re-arms the ticket.  (Round 1:
@@ -313,6 +317,137 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const float4 *__restrict__
     sorted[pos] = p;
 }
 
+// ---- small clouds: the whole counting sort in ONE launch of one thread-block cluster ------------------------------------
+// The down-sampled clouds (~9k points) get six search structures per alignment on the critical path (normals grid, FPFH
+// grid per cloud; RANSAC grid; Morton order), each a memset + three tiny kernels whose cost was launch latency, not work
+// (~35 us per build, 0.2 ms per alignment).  Eight CTAs of 1024 threads on one GPC do all four phases between hardware
+// cluster barriers (~0.2 us each): clear the table, count (cell id and arrival rank stay in registers), exclusive scan
+// (per-thread runs of cells, CTA scan, the eight CTA totals exchanged through distributed shared memory), scatter.
+constexpr int GC_CTAS = 8, GC_THREADS = 1024, GC_NT = GC_CTAS * GC_THREADS, GC_PPT = 4;
+constexpr int GC_MAX_POINTS = GC_NT * GC_PPT;          // 32,768
+constexpr long long GC_MAX_CELLS = (1LL << 20);        // 4 MB table: 128 cells per thread in the scan
+
+struct MortonDims {
+    double ox, oy, oz, inv_c;
+    int lim;  // 2^L - 1
+};
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 8 bits -> every third bit
+    v &= 0xffu;
+    v = (v | (v << 8)) & 0x00f00fu;
+    v = (v | (v << 4)) & 0x0c30c3u;
+    v = (v | (v << 2)) & 0x249249u;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t morton_of(const MortonDims &g, const float4 &p) {
+    const int cx = min(max((int)floor(((double)p.x - g.ox) * g.inv_c), 0), g.lim);
+    const int cy = min(max((int)floor(((double)p.y - g.oy) * g.inv_c), 0), g.lim);
+    const int cz = min(max((int)floor(((double)p.z - g.oz) * g.inv_c), 0), g.lim);
+    return spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+}
+
+__device__ __forceinline__ uint32_t gc_cell(const GridDims &g, const float4 &p) { return cell_of(g, p); }
+__device__ __forceinline__ uint32_t gc_cell(const MortonDims &g, const float4 &p) { return morton_of(g, p); }
+
+// start has ncells + 1 entries padded to a multiple of 4 (the pad is written, never read)
+template <typename Dims>
+__global__ void __cluster_dims__(GC_CTAS, 1, 1) __launch_bounds__(GC_THREADS) k_grid_cluster(const float4 *__restrict__ pts, int n, Dims g,
+                                                                                           long long ncells, uint32_t *__restrict__ start,
+                                                                                           float4 *__restrict__ sorted) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t s_total;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int t = rank * GC_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long len = (ncells + 1 + 3) & ~3LL;  // entries, a multiple of 4
+    // phase 0: clear
+    for (long long k = 4LL * t; k < len; k += 4LL * GC_NT) *reinterpret_cast<uint4 *>(start + k) = make_uint4(0u, 0u, 0u, 0u);
+    cluster.sync();
+    // phase 1: count
+    uint32_t c[GC_PPT], r[GC_PPT];
+#pragma unroll
+    for (int k = 0; k < GC_PPT; k++) {
+        const int i = t + k * GC_NT;
+        c[k] = r[k] = 0u;
+        if (i < n) {
+            c[k] = gc_cell(g, __ldg(pts + i));
+            r[k] = atomicAdd(start + c[k], 1u);
+        }
+    }
+    cluster.sync();
+    // phase 2: exclusive scan over `len` entries; thread t owns the run [t S, (t + 1) S), S a multiple of 4
+    const long long S = (((len + GC_NT - 1) / GC_NT) + 3) & ~3LL;
+    const long long k0 = min((long long)t * S, len), k1 = min(k0 + S, len);
+    uint32_t mine = 0;
+    for (long long k = k0; k < k1; k += 4) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(start + k));
+        mine += (v.x + v.y) + (v.z + v.w);
+    }
+    uint32_t x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = ws[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        ws[lane] = w;  // inclusive over warps
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    uint32_t run = (x - mine) + (warp ? ws[warp - 1] : 0u);  // exclusive inside this CTA
+    cluster.sync();
+    for (int q = 0; q < rank; q++) run += *cluster.map_shared_rank(&s_total, q);
+    for (long long k = k0; k < k1; k += 4) {
+        uint4 v = __ldcg(reinterpret_cast<const uint4 *>(start + k));
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run; run += v.w;
+        *reinterpret_cast<uint4 *>(start + k) = o;
+    }
+    cluster.sync();  // also keeps every CTA's s_total alive until all have read it
+    // phase 3: scatter
+#pragma unroll
+    for (int k = 0; k < GC_PPT; k++) {
+        const int i = t + k * GC_NT;
+        if (i < n) {
+            float4 p = __ldg(pts + i);
+            p.w = __int_as_float(i);
+            sorted[__ldcg(start + c[k]) + r[k]] = p;
+        }
+    }
+}
+
+static inline bool grid_small(int n, long long ncells) {
+    const char *env = getenv("PCR_GRID_CLUSTER");  // 0: always the multi-kernel build (tests compare the two)
+    if (env && atoi(env) == 0) return false;
+    return n <= GC_MAX_POINTS && ncells <= GC_MAX_CELLS;
+}
+
+template <typename Dims>
+static int grid_cluster_launch(pcr_ctx *ctx, const float4 *pts, int n, const Dims &d, long long ncells, uint32_t **start_out,
+                               float4 *sorted) {
+    const size_t len = ((size_t)ncells + 1 + 3) & ~(size_t)3;
+    uint32_t *start = arena<uint32_t>(ctx, len);
+    if (!start) return PCR_ERR_OOM;
+    k_grid_cluster<Dims><<<GC_CTAS, GC_THREADS, 0, ctx->stream>>>(pts, n, d, ncells, start, sorted);
+    PCR_LAUNCHED();
+    PCR_CUDA(cudaGetLastError());
+    *start_out = start;
+    return PCR_OK;
+}
+
 int pcr_grid_build(pcr_ctx *ctx, const float4 *pts, int n, double radius, const float *lo_in, const float *hi_in,
                    Grid *g) {
     return pcr_grid_build_rings(ctx, pts, n, radius, 1, lo_in, hi_in, g);
@@ -344,19 +479,25 @@ int pcr_grid_build_rings(pcr_ctx *ctx, const float4 *pts, int n, double radius, 
     }
     const long long ncells = nx * ny * nz;
     GridDims gd{(double)lo[0], (double)lo[1], (double)lo[2], 1.0 / h, (int)nx, (int)ny, (int)nz};
-    PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
-    uint32_t *rank = cell + n;
     PCR_ALLOC(sorted, float4, (size_t)n);
-    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
-    SortTables tb;
-    PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
-    uint32_t *start = tb.start;
-    k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, rank, start);
-    PCR_LAUNCHED();
-    PCR_TRY(sort_tables_scan(ctx, tb, ncells));
-    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
-    PCR_LAUNCHED();
-    PCR_CUDA(cudaGetLastError());
+    uint32_t *start = nullptr;
+    if (grid_small(n, ncells)) {
+        KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 1);
+        PCR_TRY(grid_cluster_launch(ctx, pts, n, gd, ncells, &start, sorted));
+    } else {
+        PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
+        uint32_t *rank = cell + n;
+        KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
+        SortTables tb;
+        PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
+        start = tb.start;
+        k_cell_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, gd, cell, rank, start);
+        PCR_LAUNCHED();
+        PCR_TRY(sort_tables_scan(ctx, tb, ncells));
+        k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
+        PCR_LAUNCHED();
+        PCR_CUDA(cudaGetLastError());
+    }
     g->sorted = sorted;
     g->start = start;
     g->ox = gd.ox; g->oy = gd.oy; g->oz = gd.oz;
@@ -512,29 +653,12 @@ int pcr_grid_build_compact(pcr_ctx *ctx, const float4 *pts, int n, double radius
 }
 
 // ---- Morton-order sort ---------------------------------------------------------------------------------------------
-struct MortonDims {
-    double ox, oy, oz, inv_c;
-    int lim;  // 2^L - 1
-};
-
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 8 bits -> every third bit
-    v &= 0xffu;
-    v = (v | (v << 8)) & 0x00f00fu;
-    v = (v | (v << 4)) & 0x0c30c3u;
-    v = (v | (v << 2)) & 0x249249u;
-    return v;
-}
-
 __global__ void __launch_bounds__(256) k_morton_count(const float4 *__restrict__ pts, int n, MortonDims g,
                                                       uint32_t *__restrict__ cell, uint32_t *__restrict__ rank,
                                                       uint32_t *__restrict__ count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 p = __ldg(pts + i);
-    const int cx = min(max((int)floor(((double)p.x - g.ox) * g.inv_c), 0), g.lim);
-    const int cy = min(max((int)floor(((double)p.y - g.oy) * g.inv_c), 0), g.lim);
-    const int cz = min(max((int)floor(((double)p.z - g.oz) * g.inv_c), 0), g.lim);
-    const uint32_t c = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+    const uint32_t c = morton_of(g, __ldg(pts + i));
     cell[i] = c;
     rank[i] = atomicAdd(count + c, 1u);
 }
@@ -552,19 +676,25 @@ int pcr_morton_sort(pcr_ctx *ctx, const float4 *pts, int n, const float4 **sorte
     while (L < 8 && (1LL << (3 * L)) < 4LL * n) L++;
     const long long ncells = 1LL << (3 * L);
     MortonDims md{(double)lo[0], (double)lo[1], (double)lo[2], ext > 0.0 ? (double)(1 << L) / (ext * (1.0 + 1e-6)) : 0.0, (1 << L) - 1};
-    PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
-    uint32_t *rank = cell + n;
     PCR_ALLOC(sorted, float4, (size_t)n);
-    KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
-    SortTables tb;
-    PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
-    uint32_t *start = tb.start;
-    k_morton_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, md, cell, rank, start);
-    PCR_LAUNCHED();
-    PCR_TRY(sort_tables_scan(ctx, tb, ncells));
-    k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
-    PCR_LAUNCHED();
-    PCR_CUDA(cudaGetLastError());
+    if (grid_small(n, ncells)) {
+        KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 1);
+        uint32_t *start = nullptr;
+        PCR_TRY(grid_cluster_launch(ctx, pts, n, md, ncells, &start, sorted));
+    } else {
+        PCR_ALLOC(cell, uint32_t, 2 * (size_t)n);
+        uint32_t *rank = cell + n;
+        KScope ks(ctx, KC_GRID_BUILD, 56.0 * n + 8.0 * (double)ncells, 3);
+        SortTables tb;
+        PCR_TRY(sort_tables_alloc(ctx, ncells, &tb));
+        uint32_t *start = tb.start;
+        k_morton_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, md, cell, rank, start);
+        PCR_LAUNCHED();
+        PCR_TRY(sort_tables_scan(ctx, tb, ncells));
+        k_cell_scatter<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, rank, start, sorted);
+        PCR_LAUNCHED();
+        PCR_CUDA(cudaGetLastError());
+    }
     *sorted_out = sorted;
     return PCR_OK;
 }

@@ -698,49 +698,76 @@ __global__ void __launch_bounds__(128) k_spfh(const float4 *__restrict__ pts, co
 }
 
 // One warp per point.  FPFH[j] = (sum_k SPFH[nb_k][j] / d2_k) * (100 / S_b) + SPFH[i][j]  with the block normaliser
-// S_b accumulated in the reference's order (neighbour-major, bin-minor).  The quotients are produced once by all
-// lanes into a shared-memory chunk; the order-sensitive fp64 additions then read them back sequentially.
-constexpr int FPFH_CHUNK = 16;
+// S_b of rule D8.  Lane j owns bin j (lane 0 also bin 32) and adds the quotients of its bin in neighbour order; a chunk of
+// FPFH_CHUNK neighbours is gathered at once — lane j reads element j of every neighbour's SPFH row (one coalesced 256-byte
+// row per load instruction, all of them in flight before the first is used), lane k reads bin 32 of neighbour k — so a
+// chunk costs ONE L2 round trip.  (Until round 2 the elements went through a shared-memory staging array one dependent
+// gather at a time: ~10k cycles per chunk on a kernel that is a single wave of warps, i.e. a pure latency chain.)
+constexpr int FPFH_CHUNK = 8;
+constexpr int FPFH_TILE = 128;  // neighbours staged per round (4 per lane); max_nn = 100 fits in one
 __global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx, const float *__restrict__ d2,
                                               const int *__restrict__ cnt, int max_nn,
                                               const double *__restrict__ spfh, float *__restrict__ out,
                                               const float4 *__restrict__ order) {
-    __shared__ double sval[4][FPFH_CHUNK][33];
-    __shared__ double sdist[4][FPFH_CHUNK], srinv[4][FPFH_CHUNK];
+    // per warp: distance, its reciprocal, neighbour index and the finished quotient of bin 32, for one tile of neighbours
+    __shared__ double s_b[4][FPFH_TILE], s_r[4][FPFH_TILE], s_q32[4][FPFH_TILE];
+    __shared__ int s_nb[4][FPFH_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double (*val)[33] = sval[warp];
     for (int is = blockIdx.x * 4 + warp; is < n; is += gridDim.x * 4) {
         const int i = __float_as_int(__ldg(order + is).w);  // cell order, as in k_spfh
         const int c = cnt[i];
         double F0 = 0.0, F1 = 0.0;  // bins `lane` and (lane 0 only) 32
         double sum = 0.0;           // lanes 0..2: normaliser of block `lane`
-        for (int k0 = 1; k0 < c; k0 += FPFH_CHUNK) {
-            const int nk = min(FPFH_CHUNK, c - k0);
+        for (int t0 = 1; t0 < c; t0 += FPFH_TILE) {
+            const int nt = min(FPFH_TILE, c - t0);
             // One correctly rounded reciprocal per neighbour, then every quotient SPFH/d2 by Markstein's sequence
             // q0 = a*r, rem = fma(-b, q0, a), q = fma(rem, r, q0): with r = RN(1/b) this IS the correctly rounded a/b
             // unless b's significand is all ones — impossible here, b is an fp32 value widened to fp64.  33 divisions
             // per neighbour become 1 division + 33 x 3 multiply-adds with identical bits (checked by the parity tests).
-            if (lane < nk) {
-                const double dist = (double)d2[(size_t)i * max_nn + k0 + lane];
-                sdist[warp][lane] = dist;
-                srinv[warp][lane] = dist == 0.0 ? 0.0 : 1.0 / dist;
+            // Staging: every lane takes 4 neighbours of the tile — index, distance, reciprocal (the divisions of the whole
+            // tile run side by side instead of one per chunk) and bin 32, which lane 0 will only have to add.
+            __syncwarp();
+            int nb4[FPFH_TILE / 32];
+            double b4[FPFH_TILE / 32];
+#pragma unroll
+            for (int g = 0; g < FPFH_TILE / 32; g++) {
+                const int k = lane + 32 * g;
+                nb4[g] = k < nt ? idx[(size_t)i * max_nn + t0 + k] : 0;
+                b4[g] = k < nt ? (double)d2[(size_t)i * max_nn + t0 + k] : 0.0;
+            }
+#pragma unroll
+            for (int g = 0; g < FPFH_TILE / 32; g++) {
+                const int k = lane + 32 * g;
+                if (k < nt) {
+                    const double a32 = __ldg(spfh + (size_t)nb4[g] * 33 + 32);
+                    const double r = b4[g] == 0.0 ? 0.0 : 1.0 / b4[g];
+                    const double q0 = a32 * r;
+                    const double rem = __fma_rn(-b4[g], q0, a32);
+                    s_nb[warp][k] = nb4[g];
+                    s_b[warp][k] = b4[g];
+                    s_r[warp][k] = r;
+                    // a zero distance (duplicate point) is skipped by the reference; adding +0.0 is the same bits
+                    s_q32[warp][k] = b4[g] == 0.0 ? 0.0 : __fma_rn(rem, r, q0);
+                }
             }
             __syncwarp();
-            for (int e = lane; e < nk * 33; e += 32) {
-                const int kk = e / 33, j = e - kk * 33;
-                const double b = sdist[warp][kk], r = srinv[warp][kk];
-                const double a = spfh[(size_t)idx[(size_t)i * max_nn + k0 + kk] * 33 + j];
-                const double q0 = a * r;
-                const double rem = __fma_rn(-b, q0, a);
-                // a zero distance (duplicate point) is skipped by the reference; adding +0.0 is the same bits
-                val[kk][j] = b == 0.0 ? 0.0 : __fma_rn(rem, r, q0);
+            for (int k0 = 0; k0 < nt; k0 += FPFH_CHUNK) {
+                const int nk = min(FPFH_CHUNK, nt - k0);
+                double a[FPFH_CHUNK];
+#pragma unroll
+                for (int kk = 0; kk < FPFH_CHUNK; kk++)
+                    a[kk] = kk < nk ? __ldg(spfh + (size_t)s_nb[warp][k0 + kk] * 33 + lane) : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < FPFH_CHUNK; kk++) {
+                    if (kk < nk) {
+                        const double b = s_b[warp][k0 + kk], r = s_r[warp][k0 + kk];
+                        const double q0 = a[kk] * r;
+                        const double rem = __fma_rn(-b, q0, a[kk]);
+                        F0 = F0 + (b == 0.0 ? 0.0 : __fma_rn(rem, r, q0));
+                        F1 = F1 + s_q32[warp][k0 + kk];
+                    }
+                }
             }
-            __syncwarp();
-            for (int kk = 0; kk < nk; kk++) {
-                F0 = F0 + val[kk][lane];
-                if (lane == 0) F1 = F1 + val[kk][32];
-            }
-            __syncwarp();
         }
         // D8: the normaliser of block b is the sum of its 11 accumulated bins in bin order (lane b gathers them by
         // shuffles; bin 32 lives in lane 0's F1).  A running sum over (neighbour, bin), as Open3D keeps it, is 1100

@@ -708,12 +708,13 @@ static void reg_result_init(pcr_reg_result *r, int64_t max_iter) {
 
 int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, int mt, const int *corr, int c,
                     double max_dist, double edge_sim, int64_t max_iter, double confidence, u64 seed,
-                    pcr_reg_result *res) {
+                    pcr_reg_result *res, const RansacWork *prepared) {
     reg_result_init(res, max_iter);
     // Open3D returns the default result for ransac_n > |corr| or a non-positive threshold (A.6)
     if (c < 3 || !(max_dist > 0.0) || ms == 0 || mt == 0 || max_iter <= 0) return PCR_OK;
     RansacWork w;
-    PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
+    if (prepared) w = *prepared;  // built ahead of time by the caller (pcr_align: next to the descriptor matching)
+    else PCR_TRY(pcr_ransac_prepare(ctx, src, ms, tgt, mt, max_dist, &w));
     std::vector<pcr_hyp_record> recs;
     static const int wave_first = getenv("PCR_WAVE_FIRST") ? atoi(getenv("PCR_WAVE_FIRST")) : 2048;
     static const int wave_growth = getenv("PCR_WAVE_GROWTH") ? atoi(getenv("PCR_WAVE_GROWTH")) : 64;

@@ -481,3 +481,19 @@ def test_compact_grid_equals_dense(orc, eng, pair, monkeypatch):
     oi, od = orc.nn1(tgt, q, 0.01)
     assert np.array_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
     assert np.array_equal(res["1"][0], oi) and np.array_equal(res["1"][1], od)
+
+
+def test_cluster_grid_build_equals_multi_kernel_build(eng, pair, monkeypatch):
+    """Small clouds build their search grids in one thread-block-cluster launch; the neighbour lists, normals and a whole
+    RANSAC run must not depend on which build produced the grid."""
+    v = pair["v"]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PCR_GRID_CLUSTER", mode)
+        idx, d2, cnt = eng.knn_hybrid(pair["sd"], pair["sd"], 5 * v, 100)
+        nrm = eng.estimate_normals(pair["td"], 2 * v, 30)
+        r = eng.ransac(pair["sd"], pair["td"], pair["corr"], 1.5 * v, 20000, 1.0, 7)
+        out[mode] = (idx.cpu().numpy(), d2.cpu().numpy(), cnt.cpu().numpy(), nrm.cpu().numpy(), np.asarray(r.transformation),
+                     np.array([r.best_hyp, r.inlier_count, r.sum_d2_fixed, r.survivors]))
+    for a, b in zip(out["1"], out["0"]):
+        assert np.array_equal(a, b)
