@@ -214,8 +214,9 @@ struct StageTimer {
 
 int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out);
 
-// Ply._preprocess of one cloud (src/ply/ply.py:106-120) on `c`: voxel grid, normals, FPFH
-static int preprocess_cloud(pcr_ctx *c, const float4 *pts, int n, double v, float4 **down, int *m, float4 **nrm, float **fpfh) {
+// Ply._preprocess of one cloud (src/ply/ply.py:106-120) on `c`, in two parts: the voxel grid (ends with a host
+// synchronisation: the number of occupied voxels), then normals + FPFH of the down-sampled cloud (fully asynchronous)
+static int preprocess_voxel(pcr_ctx *c, const float4 *pts, int n, double v, float4 **down, int *m) {
     pcr_ctx *ctx = c;
     PCR_ALLOC(d, float4, (size_t)n);
     PCR_TRY(pcr_voxel_impl(ctx, pts, n, v, d, m));
@@ -231,11 +232,16 @@ static int preprocess_cloud(pcr_ctx *c, const float4 *pts, int n, double v, floa
         for (int k = 0; k < 3; k++) { e.lo[k] = lo[k]; e.hi[k] = hi[k]; }
         ctx->bounds_cache.push_back(e);
     }
-    PCR_ALLOC(nn, float4, (size_t)*m);
-    PCR_TRY(pcr_normals_impl(ctx, d, *m, 2.0 * v, 30, nn));
-    PCR_ALLOC(f, float, (size_t)*m * 33);
-    PCR_TRY(pcr_fpfh_impl(ctx, d, nn, *m, 5.0 * v, 100, f));
     *down = d;
+    return PCR_OK;
+}
+
+static int preprocess_features(pcr_ctx *c, const float4 *d, int m, double v, float4 **nrm, float **fpfh) {
+    pcr_ctx *ctx = c;
+    PCR_ALLOC(nn, float4, (size_t)m);
+    PCR_TRY(pcr_normals_impl(ctx, d, m, 2.0 * v, 30, nn));
+    PCR_ALLOC(f, float, (size_t)m * 33);
+    PCR_TRY(pcr_fpfh_impl(ctx, d, nn, m, 5.0 * v, 100, f));
     *nrm = nn;
     *fpfh = f;
     return PCR_OK;
@@ -298,9 +304,31 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     // reductions, each with its own init kernel and host synchronisation)
     PCR_TRY(pcr_bounds_pair(ctx, src, ns, tgt, nt));
     if (overlap) h->bounds_cache = ctx->bounds_cache;
-    // (Preprocessing the two clouds concurrently was measured and gains nothing: each of its kernels fills the GPU.)
-    int rc = preprocess_cloud(ctx, src, ns, v, &sd, &ms, &sn, &sf);
-    if (rc == PCR_OK) rc = preprocess_cloud(ctx, tgt, nt, v, &td, &mt, &tn, &tf);
+    // Both voxel grids first (each ends with a host synchronisation), then normals + FPFH of the two down-sampled clouds
+    // side by side on the main and the auxiliary stream: they are chains of small, latency-bound kernels over ~9k points
+    // (one to two waves of CTAs each) whose tails leave most of the GPU idle.  PCR_PRE_CONCURRENT=0: one after the other.
+    static const bool pre_conc = !(getenv("PCR_PRE_CONCURRENT") && atoi(getenv("PCR_PRE_CONCURRENT")) == 0);
+    int rc = preprocess_voxel(ctx, src, ns, v, &sd, &ms);
+    if (rc == PCR_OK) rc = preprocess_voxel(ctx, tgt, nt, v, &td, &mt);
+    if (rc == PCR_OK) {
+        if (overlap && pre_conc && ctx->aux_stream) {
+            cudaEvent_t ev;
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            cudaEventRecord(ev, ctx->stream);
+            cudaStreamWaitEvent(ctx->aux_stream, ev, 0);
+            cudaStream_t keep = ctx->stream;
+            ctx->stream = ctx->aux_stream;
+            rc = preprocess_features(ctx, td, mt, v, &tn, &tf);
+            ctx->stream = keep;
+            cudaEventRecord(ev, ctx->aux_stream);
+            if (rc == PCR_OK) rc = preprocess_features(ctx, sd, ms, v, &sn, &sf);
+            cudaStreamWaitEvent(ctx->stream, ev, 0);
+            cudaEventDestroy(ev);
+        } else {
+            rc = preprocess_features(ctx, sd, ms, v, &sn, &sf);
+            if (rc == PCR_OK) rc = preprocess_features(ctx, td, mt, v, &tn, &tf);
+        }
+    }
     if (rc != PCR_OK) {
         if (ready) cudaEventDestroy(ready);
         return rc;
