@@ -142,6 +142,7 @@ struct pcr_ctx {
     pcr_ctx *helper = nullptr;
     struct Worker *worker = nullptr;
     bool owns_stream = false;
+    int yielding = 0;  // > 0: this context runs beside a critical path; its long kernels use CTAs of `yielding` queries per warp
     void *dist = nullptr;              // multi-GPU state (pcr_dist.cu): NCCL communicator, exchange buffers, worker contexts
     cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
     cudaStream_t aux_stream = nullptr; // second highest-priority stream: work pcr_align issues next to its critical path

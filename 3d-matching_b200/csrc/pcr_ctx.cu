@@ -153,6 +153,7 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
             return pcr_fail(ctx, PCR_ERR_CUDA, "cannot create the helper stream");
         }
         h->owns_stream = true;
+        h->yielding = getenv("PCR_HELPER_YIELD") ? atoi(getenv("PCR_HELPER_YIELD")) : 2;
         int prio_low = 0, prio_high = 0;
         cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
         if (cudaStreamCreateWithPriority(&ctx->hp_stream, cudaStreamNonBlocking, prio_high) != cudaSuccess) {

@@ -796,7 +796,14 @@ __global__ void __launch_bounds__(128) k_fpfh(int n, const int *__restrict__ idx
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-static int knn_blocks(pcr_ctx *ctx, int nq) { return min(div_up(nq, KNN_WARPS), ctx->sm_count * 16); }
+// A context that works NEXT TO a critical path (pcr_align's helper) launches short-lived CTAs, a few queries each, instead
+// of a persistent grid: CTA slots then free up all the time and the block scheduler hands them to the higher-priority
+// stream first — a persistent grid never retires a CTA, so stream priorities had nothing to act on and the descriptor
+// matching ran at half speed beside the full-resolution normals (tools/gpu_timeline.py).
+static int knn_blocks(pcr_ctx *ctx, int nq) {
+    if (ctx->yielding) return div_up(nq, KNN_WARPS * ctx->yielding);
+    return min(div_up(nq, KNN_WARPS), ctx->sm_count * 16);
+}
 
 int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq, double radius, int max_nn, int *idx,
                  float *d2, int *cnt) {
