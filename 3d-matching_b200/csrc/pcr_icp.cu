@@ -16,13 +16,13 @@
 
 struct IcpState {
     double T[16];
-    long long acc3[3][32];  // triple-buffered: 0..20 JtJ upper triangle (row-major), 21..26 Jtr, 27 count, 28 sum d2
     unsigned int bar;       // grid-barrier arrival counter
     int pass;
     int done;
     int iterations;
     int converged;
     int max_iter;
+    int cert_pass;         // first pass whose searches also produce certificates (PCR_ICP_CERT_PASS, default ICP_CERT_PASS)
     double prev_fit, prev_rmse;
     double fitness, rmse;
     long long count, sumq;
@@ -31,6 +31,12 @@ struct IcpState {
     double isc_JJ, isc_Jr, isc_d;    // 2^-2(kq - e_J), 2^-((kq - e_J) + (kq - e_R)), 2^-k_d
     double T_out[16];
     int trace;             // PCR_ICP_TRACE=1: collect the cycle counters below (two extra atomics per CTA and pass)
+    // triple-buffered sums: 0..20 JtJ upper triangle (row-major), 21..26 Jtr, 27 count, 28 sum d2.  One 256-byte block per
+    // sum (ICP_ACC_STRIDE words): every CTA adds its 29 partial sums once per pass, and atomics on one address — and on the two
+    // 128-byte lines of a pair, which share an L2 slice — are applied one after the other (tools/micro/barrier_bench2.cu:
+    // exchange + barrier of 592 CTAs 7,736 -> 5,883 cycles, 392 CTAs 5,595 -> 4,524)
+    // (placed after the header: the host copies header + sums to the device, and only the header back)
+    long long acc3[3][29 * 32 /* ICP_ACC_STRIDE */];
     long long dbgsearch[64];  // per-pass number of points that took the search path / the second tier (PCR_ICP_TRACE)
     long long dbgtier2[64];
     long long dbgmax[64];  // per-pass slowest CTA loop
@@ -205,7 +211,8 @@ constexpr int ICP_WARPS = ICP_THREADS / 32;
 #ifndef PCR_ICP_CERT_PASS
 #define PCR_ICP_CERT_PASS 2
 #endif
-constexpr int ICP_CERT_PASS = PCR_ICP_CERT_PASS;
+constexpr int ICP_CERT_PASS = PCR_ICP_CERT_PASS;  // default; PCR_ICP_CERT_PASS in the environment overrides it per call
+constexpr int ICP_ACC_STRIDE = 32;                 // 8-byte words between two of the 29 sums (one 256-byte block each)
 
 // Result of the correspondence step for one source point: target index (-1: none), fp32 squared distance, and the
 // matched target point and normal.
@@ -237,25 +244,38 @@ struct IcpMatch {
 // the nearest two; the winner of the exact (d2, index) key comparison between j and j2 is kept if it beats w3 as above.
 // Passes 0..1 use the cheaper pruned search while the cloud still moves (no certificate is read before pass 3).
 // All bound comparisons carry a 2e-5 relative slack on both sides, orders of magnitude above the fp32 rounding of
-// the distances involved, so a certified answer is always the exact answer.
+// the distances involved, so a certified answer is always the exact answer (icp_cert_ok: the comparison in squared form).
+// a + b < s with a 2e-5 relative slack on both sides, from the SQUARES a2, b2, s2 (all >= 0), without a square root:
+//   a + b < s  <=>  R := s^2 - a^2 - b^2 > 0  and  4 a^2 b^2 < R^2.
+// With A = 1.00004 a2, B = 1.00004 b2, S = 0.99996 s2 the computed R = (S - A) - B is off by at most 3e-7 S, while the
+// un-slacked s^2 - a^2 - b^2 exceeds the exact S - A - B by 4e-5 (S + A + B): a passing test implies the exact
+// inequality.  S > 1e-16 keeps R^2 and 4AB clear of the denormal range (distances of 1e-8: never met; such a point takes
+// the search).  The test only decides between reuse and search — both give the same answer — so it may be as strict as
+// it likes; it replaces three correctly rounded sqrtf (MUFU.RSQ + Newton step + slow-path branch each) per point and pass.
+__device__ __forceinline__ bool icp_cert_ok(float a2, float b2, float s2) {
+    const float A = __fmul_rn(a2, 1.00004f), B = __fmul_rn(b2, 1.00004f), S = __fmul_rn(s2, 0.99996f);
+    const float R = __fsub_rn(__fsub_rn(S, A), B);
+    return R > 0.0f && S > 1e-16f && __fmul_rn(__fmul_rn(4.0f, A), B) < __fmul_rn(R, R);
+}
+
 __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__restrict__ tgt, const float4 *__restrict__ nrm, float3 q,
-                                             float r2, float max_dist_f, int pass, int i, IcpState *__restrict__ trc,
+                                             float r2, float max_dist2_f, int cert_pass, int pass, int i, IcpState *__restrict__ trc,
                                              float4 *__restrict__ st0, float4 *__restrict__ st1, float4 *__restrict__ st2,
                                              float4 *__restrict__ cert2, IcpMatch &o) {
-    if (pass > ICP_CERT_PASS) {
+    if (pass > cert_pass) {
         const float4 c = st0[i], a = st1[i], b = st2[i];
         // second tier: ONE coalesced 16-byte record (the second candidate's position and index; its bound w3 rides in
         // st2.w) read on demand — it used to be (j2, w3) + a gather of tgt[j2], two chained misses for the 0.5 % of the
         // points that take this tier in every steady pass
         const float mx = q.x - c.x, my = q.y - c.y, mz = q.z - c.z;
-        const float delta = sqrtf((mx * mx + my * my) + mz * mz);
+        const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz));  // |q - q_ref|^2
         if (c.w > 0.0f) {
             const int j_old = __float_as_int(a.w);
             const float d1 = dist2f(q.x, q.y, q.z, a.x, a.y, a.z);
             o.tx = a.x; o.ty = a.y; o.tz = a.z; o.nx = b.x; o.ny = b.y; o.nz = b.z;
             // (a certified nearest point that has drifted out of the radius takes the search path, which then
             // records a "no correspondence" certificate)
-            if (d1 < r2 && (sqrtf(d1) + delta) * 1.00002f < sqrtf(c.w) * 0.99998f) {
+            if (d1 < r2 && icp_cert_ok(d1, m2, c.w)) {
                 o.j = j_old;
                 o.d2 = d1;
                 return;
@@ -271,7 +291,7 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
                 const u64k kb = (((u64k)__float_as_uint(d2b)) << 32) | (uint32_t)j2;
                 const bool a_wins = ka < kb;  // exactly the comparison the search makes between these two
                 const float dw = a_wins ? d1 : d2b;
-                if (dw < r2 && (sqrtf(dw) + delta) * 1.00002f < sqrtf(w3) * 0.99998f) {
+                if (dw < r2 && icp_cert_ok(dw, m2, w3)) {
                     if (!a_wins) {
                         // the pair swaps roles: w no longer bounds "all points but the nearest", so it is set to a
                         // value that always defers to this tier; w3 bounds every point outside the pair as before
@@ -288,7 +308,7 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
                 }
             }
         } else if (c.w < 0.0f) {
-            if ((max_dist_f + delta) * 1.00002f < sqrtf(-c.w) * 0.99998f) {
+            if (icp_cert_ok(max_dist2_f, m2, -c.w)) {
                 o.j = -1;
                 o.d2 = 0.0f;
                 return;
@@ -298,7 +318,7 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
     float d2, other = 0.0f, third = 0.0f;
     int j, j2 = -1;
     if (trc && pass < 64) atomicAdd((unsigned long long *)&trc->dbgsearch[pass], 1ull);
-    if (pass >= ICP_CERT_PASS) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
+    if (pass >= cert_pass) j = grid_nn1_cert(g, q.x, q.y, q.z, r2, &d2, &other, &j2, &third);
     else j = grid_nn1(g, q.x, q.y, q.z, r2, &d2);
     o.j = j;
     o.d2 = d2;
@@ -306,7 +326,7 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
         const float4 tp = __ldg(tgt + j), np = __ldg(nrm + j);
         o.tx = tp.x; o.ty = tp.y; o.tz = tp.z; o.nx = np.x; o.ny = np.y; o.nz = np.z;
         st1[i] = make_float4(tp.x, tp.y, tp.z, __int_as_float(j));
-        if (pass >= ICP_CERT_PASS) {
+        if (pass >= cert_pass) {
             float4 t2 = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
             if (j2 >= 0) {
                 t2 = __ldg(tgt + j2);
@@ -319,7 +339,34 @@ __device__ __forceinline__ void icp_point_nn(const Grid &g, const float4 *__rest
     } else {
         st1[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
         // nothing inside the radius: every target point is at least min(nearest examined, h) away
-        if (pass >= ICP_CERT_PASS) st0[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
+        if (pass >= cert_pass) st0[i] = make_float4(q.x, q.y, q.z, -fminf(d2, other));
+    }
+}
+
+// Accumulate phase of one warp and chunk: the sums of entry group GRP (7 / 6 / 7 / 7 of the 27 products) over 4 of the
+// 128 staged rows of the warp's group (see k_icp_persist).
+template <int GRP>
+__device__ __forceinline__ void icp_accumulate(const int (*__restrict__ rw)[ICP_THREADS], int row0, long long (&acc)[7]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = row0 + 32 * k;
+        const long long v3 = rw[3][r], v4 = rw[4][r], v5 = rw[5][r], v6 = rw[6][r];
+        if (GRP == 0) {
+            const long long v0 = rw[0][r], v1 = rw[1][r], v2 = rw[2][r];
+            acc[0] += v0 * v0; acc[1] += v0 * v1; acc[2] += v0 * v2; acc[3] += v0 * v3;
+            acc[4] += v0 * v4; acc[5] += v0 * v5; acc[6] += v0 * v6;
+        } else if (GRP == 1) {
+            const long long v1 = rw[1][r], v2 = rw[2][r];
+            acc[0] += v1 * v1; acc[1] += v1 * v2; acc[2] += v1 * v3; acc[3] += v1 * v4;
+            acc[4] += v1 * v5; acc[5] += v1 * v6;
+        } else if (GRP == 2) {
+            const long long v2 = rw[2][r];
+            acc[0] += v2 * v2; acc[1] += v2 * v3; acc[2] += v2 * v4; acc[3] += v2 * v5;
+            acc[4] += v2 * v6; acc[5] += v5 * v5; acc[6] += v5 * v6;
+        } else {
+            acc[0] += v3 * v3; acc[1] += v3 * v4; acc[2] += v3 * v5; acc[3] += v3 * v6;
+            acc[4] += v4 * v4; acc[5] += v4 * v5; acc[6] += v4 * v6;
+        }
     }
 }
 
@@ -392,8 +439,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
     const double scd = S->sc_d;
     const float scJf = (float)S->sc_J, scRf = (float)S->sc_R;  // powers of two: exact in fp32
     const double isc_JJ = S->isc_JJ, isc_Jr = S->isc_Jr, isc_d = S->isc_d, rel_fit = S->rel_fit, rel_rmse = S->rel_rmse;
-    const int max_iter = S->max_iter, trace = S->trace;
-    const float max_dist_f = sqrtf(r2) * 1.000001f;  // >= max_dist (r2 is the fp32 rounding of max_dist^2)
+    const int max_iter = S->max_iter, trace = S->trace, cert_pass = S->cert_pass;
+    const float max_dist2_f = r2 * 1.000002f;  // >= max_dist^2 (r2 is the fp32 rounding of max_dist^2)
     const int grp = warp & 3;                       // entry group of this warp
     const int row0 = (warp >> 2) * 128 + lane;      // rows row0 + 32 k, k = 0..3 (each group of 4 warps owns 128 rows)
     __syncthreads();
@@ -413,7 +460,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
                 const float4 p = __ldg(src + i);
                 const float3 q = xform_pt(T, p.x, p.y, p.z);
                 IcpMatch m;
-                icp_point_nn(g, tgt, nrm, q, r2, max_dist_f, pass, i, trace ? S : nullptr, st0, st1, st2, cert2, m);
+                icp_point_nn(g, tgt, nrm, q, r2, max_dist2_f, cert_pass, pass, i, trace ? S : nullptr, st0, st1, st2, cert2, m);
                 if (m.j >= 0) {
                     // point-to-plane row in fp32, every operation individually rounded (as the oracle): J and r are
                     // quantised to kq <= 30 bits right here, so fp64 bought nothing but fp64-pipe time
@@ -440,26 +487,12 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
             // (Handing the 128-point units out dynamically, per group, by an atomic ticket was measured too: -1.5 % at
             // 1M points, +10 % at 100k, where every group has a single unit anyway — not kept.)
             icp_group_barrier(warp >> 2);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int r = row0 + 32 * k;
-                const long long v3 = rw[3][r], v4 = rw[4][r], v5 = rw[5][r], v6 = rw[6][r];
-                if (grp == 0) {
-                    const long long v0 = rw[0][r], v1 = rw[1][r], v2 = rw[2][r];
-                    acc[0] += v0 * v0; acc[1] += v0 * v1; acc[2] += v0 * v2; acc[3] += v0 * v3;
-                    acc[4] += v0 * v4; acc[5] += v0 * v5; acc[6] += v0 * v6;
-                } else if (grp == 1) {
-                    const long long v1 = rw[1][r], v2 = rw[2][r];
-                    acc[0] += v1 * v1; acc[1] += v1 * v2; acc[2] += v1 * v3; acc[3] += v1 * v4;
-                    acc[4] += v1 * v5; acc[5] += v1 * v6;
-                } else if (grp == 2) {
-                    const long long v2 = rw[2][r];
-                    acc[0] += v2 * v2; acc[1] += v2 * v3; acc[2] += v2 * v4; acc[3] += v2 * v5;
-                    acc[4] += v2 * v6; acc[5] += v5 * v5; acc[6] += v5 * v6;
-                } else {
-                    acc[0] += v3 * v3; acc[1] += v3 * v4; acc[2] += v3 * v5; acc[3] += v3 * v6;
-                    acc[4] += v4 * v4; acc[5] += v4 * v5; acc[6] += v4 * v6;
-                }
+            // (the entry group is uniform over the warp: one switch per chunk, not one per row)
+            switch (grp) {
+                case 0: icp_accumulate<0>(rw, row0, acc); break;
+                case 1: icp_accumulate<1>(rw, row0, acc); break;
+                case 2: icp_accumulate<2>(rw, row0, acc); break;
+                default: icp_accumulate<3>(rw, row0, acc); break;
             }
         }
         // CTA reduction, then one atomic per sum and CTA into the pass's accumulator
@@ -519,7 +552,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
 #pragma unroll
                 for (int w = 0; w < ICP_WARPS; w++) sum += red[w][sl];
             }
-            if (sum != 0) atomicAdd((unsigned long long *)&gacc[e], (unsigned long long)sum);
+            if (sum != 0) atomicAdd((unsigned long long *)&gacc[e * ICP_ACC_STRIDE], (unsigned long long)sum);
         }
         const long long cb = clock64();
         if (trace && threadIdx.x == 0 && pass < 64) atomicMax((unsigned long long *)&S->dbgmax[pass], (unsigned long long)(c1 - c0));
@@ -531,7 +564,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
         icp_grid_barrier(&S->bar, (unsigned int)(pass + 1) * gridDim.x);
         const long long ce = clock64();
         if (threadIdx.x < 29) {
-            const long long v = __ldcg(&gacc[threadIdx.x]);
+            const long long v = __ldcg(&gacc[threadIdx.x * ICP_ACC_STRIDE]);
             tot[threadIdx.x] = v;
             const int e = threadIdx.x;
             if (e < 21) {
@@ -545,7 +578,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_persist(co
             }
         }
         // the buffer of pass - 1 was read by every CTA before it arrived at this barrier; it is next used in pass + 2
-        if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 29) S->acc3[(pass + 2) % 3][threadIdx.x - 32] = 0;
+        if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + 29) S->acc3[(pass + 2) % 3][(threadIdx.x - 32) * ICP_ACC_STRIDE] = 0;
         __syncthreads();
         const long long c2 = clock64();
         if (threadIdx.x == 0) icp_end_solve(&E, tot, fA, fb);
@@ -668,6 +701,8 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     for (int i = 0; i < 16; i++) hS->T[i] = init[i];
     hS->max_iter = max_iter;
     hS->trace = getenv("PCR_ICP_TRACE") ? 1 : 0;
+    hS->cert_pass = getenv("PCR_ICP_CERT_PASS") ? atoi(getenv("PCR_ICP_CERT_PASS")) : ICP_CERT_PASS;
+    if (hS->cert_pass < 0) hS->cert_pass = 0;
     hS->rel_fit = rel_fit;
     hS->rel_rmse = rel_rmse;
     hS->sc_J = ldexp(1.0, s_J); hS->isc_JJ = ldexp(1.0, -2 * s_J);
@@ -678,8 +713,9 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_ALLOC(st1, float4, (size_t)ns);
     PCR_ALLOC(st2, float4, (size_t)ns);
     PCR_ALLOC(cert2, float4, (size_t)ns);
-    const size_t state_bytes = hS->trace ? sizeof(IcpState) : offsetof(IcpState, dbgcta);
-    PCR_CUDA(cudaMemcpyAsync(dS, hS, state_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t state_bytes = hS->trace ? sizeof(IcpState) : offsetof(IcpState, acc3);                 // device -> host
+    const size_t init_bytes = hS->trace ? sizeof(IcpState) : offsetof(IcpState, dbgsearch);             // host -> device: + zeroed sums
+    PCR_CUDA(cudaMemcpyAsync(dS, hS, init_bytes, cudaMemcpyHostToDevice, ctx->stream));
     float r2 = (float)(max_dist * max_dist);
     // cooperative launch: every CTA must be resident (the kernel synchronises the grid once per pass)
     int &occ = ctx->occ_icp;
