@@ -17,6 +17,7 @@ int pcr_knn_impl(pcr_ctx *ctx, const float4 *pts, int n, const float4 *q, int nq
 int pcr_normals_impl(pcr_ctx *ctx, const float4 *pts, int n, double radius, int max_nn, float4 *normals);
 int pcr_fpfh_impl(pcr_ctx *ctx, const float4 *pts, const float4 *nrm, int n, double radius, int max_nn, float *out);
 int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, int *m_host);
+int pcr_voxel_enqueue(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, unsigned long long *h_total);
 int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn);
 int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int mt, int mutual, double mutual_ratio,
                    int *corr, int *c_host);
@@ -214,25 +215,29 @@ struct StageTimer {
 
 int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out);
 
-// Ply._preprocess of one cloud (src/ply/ply.py:106-120) on `c`, in two parts: the voxel grid (ends with a host
-// synchronisation: the number of occupied voxels), then normals + FPFH of the down-sampled cloud (fully asynchronous)
-static int preprocess_voxel(pcr_ctx *c, const float4 *pts, int n, double v, float4 **down, int *m) {
+// Ply._preprocess of one cloud (src/ply/ply.py:106-120) on `c`, in two parts: the voxel grid (its size comes back through
+// one pinned word, *h_total >> 32, valid once c->stream has been synchronised), then normals + FPFH of the down-sampled
+// cloud (fully asynchronous)
+static int preprocess_voxel_enqueue(pcr_ctx *c, const float4 *pts, int n, double v, float4 **down, unsigned long long *h_total) {
     pcr_ctx *ctx = c;
     PCR_ALLOC(d, float4, (size_t)n);
-    PCR_TRY(pcr_voxel_impl(ctx, pts, n, v, d, m));
-    {
-        // the voxel centroids lie inside the bounding box of the cloud they average: that box (cached by the voxel
-        // stage) serves as the box of the search grids over the down-sampled cloud — grids are only search structures,
-        // no result depends on their origin — and saves a reduction + host synchronisation per cloud
-        float lo[3], hi[3];
-        PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));  // cache hit
-        pcr_ctx::BoundsEntry e;
-        e.ptr = d;
-        e.n = *m;
-        for (int k = 0; k < 3; k++) { e.lo[k] = lo[k]; e.hi[k] = hi[k]; }
-        ctx->bounds_cache.push_back(e);
-    }
+    PCR_TRY(pcr_voxel_enqueue(ctx, pts, n, v, d, h_total));
     *down = d;
+    return PCR_OK;
+}
+
+static int preprocess_voxel_finish(pcr_ctx *c, const float4 *pts, int n, const float4 *d, int m) {
+    pcr_ctx *ctx = c;
+    // the voxel centroids lie inside the bounding box of the cloud they average: that box (cached by the voxel
+    // stage) serves as the box of the search grids over the down-sampled cloud — grids are only search structures,
+    // no result depends on their origin — and saves a reduction + host synchronisation per cloud
+    float lo[3], hi[3];
+    PCR_TRY(pcr_bounds(ctx, pts, n, lo, hi));  // cache hit
+    pcr_ctx::BoundsEntry e;
+    e.ptr = d;
+    e.n = m;
+    for (int k = 0; k < 3; k++) { e.lo[k] = lo[k]; e.hi[k] = hi[k]; }
+    ctx->bounds_cache.push_back(e);
     return PCR_OK;
 }
 
@@ -308,8 +313,37 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     // side by side on the main and the auxiliary stream: they are chains of small, latency-bound kernels over ~9k points
     // (one to two waves of CTAs each) whose tails leave most of the GPU idle.  PCR_PRE_CONCURRENT=0: one after the other.
     static const bool pre_conc = !(getenv("PCR_PRE_CONCURRENT") && atoi(getenv("PCR_PRE_CONCURRENT")) == 0);
-    int rc = preprocess_voxel(ctx, src, ns, v, &sd, &ms);
-    if (rc == PCR_OK) rc = preprocess_voxel(ctx, tgt, nt, v, &td, &mt);
+    // The two voxel grids run side by side as well (main + auxiliary stream; one host wait for both sizes): each is a chain
+    // of five small kernels (~50 us) that used to end in its own synchronisation.
+    int rc;
+    {
+        unsigned long long *h_tot = (unsigned long long *)ctx->pinned;  // two slots
+        const bool two = overlap && pre_conc && ctx->aux_stream;
+        if (two) {
+            cudaEvent_t ev;
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            cudaEventRecord(ev, ctx->stream);  // the inputs are complete on the main stream (the bounds were read back)
+            cudaStreamWaitEvent(ctx->aux_stream, ev, 0);
+            cudaEventDestroy(ev);
+        }
+        rc = preprocess_voxel_enqueue(ctx, src, ns, v, &sd, &h_tot[0]);
+        if (rc == PCR_OK) {
+            cudaStream_t keep = ctx->stream;
+            if (two) ctx->stream = ctx->aux_stream;
+            rc = preprocess_voxel_enqueue(ctx, tgt, nt, v, &td, &h_tot[1]);
+            ctx->stream = keep;
+            if (two && cudaStreamSynchronize(ctx->aux_stream) != cudaSuccess && rc == PCR_OK)
+                rc = pcr_fail(ctx, PCR_ERR_CUDA, "voxel grid (auxiliary stream): %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == PCR_OK)
+            rc = pcr_fail(ctx, PCR_ERR_CUDA, "voxel grid: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == PCR_OK) {
+            ms = (int)(h_tot[0] >> 32);
+            mt = (int)(h_tot[1] >> 32);
+            rc = preprocess_voxel_finish(ctx, src, ns, sd, ms);
+        }
+        if (rc == PCR_OK) rc = preprocess_voxel_finish(ctx, tgt, nt, td, mt);
+    }
     if (rc == PCR_OK) {
         if (overlap && pre_conc && ctx->aux_stream) {
             cudaEvent_t ev;
@@ -339,13 +373,38 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     // Ply._add_normals on the full-resolution clouds (src/ply/ply.py:65,133-135): next to matching + RANSAC
     IcpPrep icp_prep;
     pcr_ctx *const main_ctx = ctx;
+    // ICP needs the target normals and its search structures, not the source normals (Ply.__init__ estimates them on every
+    // cloud, point-to-plane ICP never reads them): the helper raises `icp_ready` (a CUDA event on its stream + a host flag
+    // once the event has been recorded) after the former, and the main stream waits for THAT — on the device, without a
+    // host wake-up — while the source normals finish beside the first ICP passes; the call still ends only when the
+    // helper is done.
+    std::atomic<int> *phase = new std::atomic<int>(0);  // 0: not yet, 1: icp_ready recorded, 2: failed before it
+    cudaEvent_t icp_ready = nullptr;
+    struct PhaseGuard {  // destroyed after the helper has been joined (declared before the join guard)
+        std::atomic<int> *p;
+        cudaEvent_t *ev;
+        ~PhaseGuard() {
+            delete p;
+            if (*ev) cudaEventDestroy(*ev);
+        }
+    } phase_guard{phase, &icp_ready};
+    if (overlap) PCR_CUDA(cudaEventCreateWithFlags(&icp_ready, cudaEventDisableTiming));
     auto full_normals = [=, &tfn, &icp_prep](pcr_ctx *c) -> int {
         pcr_ctx *ctx = c;
-        PCR_ALLOC(t, float4, (size_t)nt);
-        PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, t));
-        tfn = t;
-        // the ICP search structures depend only on the clouds: built here, off the critical path
-        if (c != main_ctx) PCR_TRY(pcr_icp_prepare(ctx, src, ns, tgt, nt, 0.4 * v, &icp_prep));
+        auto part1 = [&]() -> int {
+            PCR_ALLOC(t, float4, (size_t)nt);
+            PCR_TRY(pcr_normals_impl(ctx, tgt, nt, 2.0 * v, 30, t));
+            tfn = t;
+            // the ICP search structures depend only on the clouds: built here, off the critical path
+            if (c != main_ctx) PCR_TRY(pcr_icp_prepare(ctx, src, ns, tgt, nt, 0.4 * v, &icp_prep));
+            return PCR_OK;
+        };
+        const int r1 = part1();
+        if (c != main_ctx) {
+            if (r1 == PCR_OK && cudaEventRecord(icp_ready, ctx->stream) == cudaSuccess) phase->store(1, std::memory_order_release);
+            else phase->store(2, std::memory_order_release);
+        }
+        if (r1 != PCR_OK) return r1;
         if (p->source_normals) {
             PCR_ALLOC(sfn, float4, (size_t)ns);
             PCR_TRY(pcr_normals_impl(ctx, src, ns, 2.0 * v, 30, sfn));
@@ -356,10 +415,19 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
         ctx->worker->submit([=]() -> int {
             cudaSetDevice(h->device);
             const int r = full_normals(h);
+            if (phase->load(std::memory_order_acquire) == 0) phase->store(2, std::memory_order_release);
             if (r != PCR_OK) return r;
             return cudaStreamSynchronize(h->stream) == cudaSuccess ? PCR_OK : PCR_ERR_CUDA;
         });
     }
+    // the helper's job refers to locals of this call: it is joined on EVERY return path
+    struct JoinGuard {
+        Worker *w;
+        bool armed;
+        ~JoinGuard() {
+            if (armed) w->wait();
+        }
+    } join_guard{overlap ? ctx->worker : nullptr, overlap};
     // The RANSAC search structures (target grid, Morton-ordered source, candidate lists: ~150 us of small kernels with no
     // host synchronisation) depend only on the down-sampled clouds: they are built on an auxiliary stream NEXT TO the
     // descriptor matching instead of between matching and RANSAC (timeline: tools/gpu_timeline.py).
@@ -397,19 +465,41 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
         rc = pcr_ransac_impl(ctx, sd, ms, td, mt, corr, c, 1.5 * v, 0.9, p->ransac_max_iter, p->ransac_confidence, p->seed, &res->ransac,
                              rwork_ok ? &rwork : nullptr);
     tm.mark();
-    if (overlap) {
+    static const bool icp_early = !(getenv("PCR_ICP_EARLY") && atoi(getenv("PCR_ICP_EARLY")) == 0);
+    auto join_helper = [&]() -> int {
+        if (!join_guard.armed) return PCR_OK;
+        join_guard.armed = false;
         const int rch = ctx->worker->wait();
-        if (rc == PCR_OK && rch != PCR_OK) rc = pcr_fail(ctx, rch, "full-resolution normals: %s", h->err.c_str());
+        return rch == PCR_OK ? PCR_OK : pcr_fail(ctx, rch, "full-resolution normals: %s", h->err.c_str());
+    };
+    if (overlap) {
+        if (rc == PCR_OK && icp_early) {
+            int ph;
+            while ((ph = phase->load(std::memory_order_acquire)) == 0) std::this_thread::yield();  // host-side enqueueing only
+            if (ph == 1) PCR_CUDA(cudaStreamWaitEvent(ctx->stream, icp_ready, 0));
+            else {
+                const int rj = join_helper();
+                rc = rj != PCR_OK ? rj : pcr_fail(ctx, PCR_ERR_CUDA, "full-resolution normals: the helper could not record its event");
+            }
+        } else {
+            const int rj = join_helper();
+            if (rc == PCR_OK) rc = rj;
+        }
     } else if (rc == PCR_OK) {
         rc = full_normals(ctx);
     }
-    if (ready) cudaEventDestroy(ready);
-    if (rc != PCR_OK) return rc;
     tm.mark();
     // refine_registration (src/matcher/icp.py:41-48): full-resolution clouds, threshold 0.4 v
-    PCR_TRY(pcr_icp_impl(ctx, src, ns, tgt, tfn, nt, 0.4 * v, res->ransac.transformation, p->icp_max_iter,
-                         p->icp_rel_fitness, p->icp_rel_rmse, &res->icp, nullptr, true, &icp_prep));
+    if (rc == PCR_OK)
+        rc = pcr_icp_impl(ctx, src, ns, tgt, tfn, nt, 0.4 * v, res->ransac.transformation, p->icp_max_iter, p->icp_rel_fitness,
+                          p->icp_rel_rmse, &res->icp, nullptr, true, &icp_prep);
     tm.mark();
+    {
+        const int rj = join_helper();
+        if (rc == PCR_OK) rc = rj;
+    }
+    if (ready) cudaEventDestroy(ready);
+    if (rc != PCR_OK) return rc;
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     res->n_src_down = ms;
     res->n_tgt_down = mt;

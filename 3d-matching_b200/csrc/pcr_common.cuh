@@ -146,6 +146,7 @@ struct pcr_ctx {
     void *dist = nullptr;              // multi-GPU state (pcr_dist.cu): NCCL communicator, exchange buffers, worker contexts
     cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
     cudaStream_t aux_stream = nullptr; // second highest-priority stream: work pcr_align issues next to its critical path
+    cudaStream_t aux2_stream = nullptr; // third: the target -> source direction of the descriptor matching (pcr_match.cu)
 };
 
 // one persistent host thread executing one task at a time

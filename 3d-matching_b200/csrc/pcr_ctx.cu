@@ -164,6 +164,10 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
             cudaGetLastError();
             ctx->aux_stream = nullptr;
         }
+        if (cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_high) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->aux2_stream = nullptr;
+        }
         ctx->helper = h;
         ctx->worker = new Worker();
     }
@@ -225,6 +229,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
     delete ctx;
     return PCR_OK;
 }

@@ -98,12 +98,40 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
     *c_host = 0;
     if (ms == 0 || mt == 0) return PCR_OK;
     PCR_ALLOC(nn_s, int, (size_t)ms);
-    PCR_TRY(pcr_nn_features_impl(ctx, fs, ms, ft, mt, nn_s));
+    PCR_ALLOC(nn_t, int, mutual ? (size_t)mt : 1);
+    // The two directions of the mutual filter are independent chains of six launches each (operand preparation, two
+    // tensor-core passes, pick, final choice, fallback): side by side on two streams when the context has them (created
+    // with pcr_align's helper; PCR_MATCH_CONCURRENT=0: one after the other).  The tensor-core kernels still take turns —
+    // a CTA holds all 512 TMEM columns of its SM — but each direction's small kernels run beside the other's GEMM.
+    static const bool conc = !(getenv("PCR_MATCH_CONCURRENT") && atoi(getenv("PCR_MATCH_CONCURRENT")) == 0);
+    cudaEvent_t t_done = nullptr;
+    if (mutual && conc && ctx->aux2_stream && ctx->aux2_stream != ctx->stream) {
+        cudaEvent_t in_ready;
+        PCR_CUDA(cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(in_ready, ctx->stream));
+        PCR_CUDA(cudaStreamWaitEvent(ctx->aux2_stream, in_ready, 0));
+        PCR_CUDA(cudaEventDestroy(in_ready));
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = ctx->aux2_stream;
+        const int rc2 = pcr_nn_features_impl(ctx, ft, mt, fs, ms, nn_t);
+        ctx->stream = keep;
+        PCR_TRY(rc2);
+        PCR_CUDA(cudaEventCreateWithFlags(&t_done, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventRecord(t_done, ctx->aux2_stream));
+    }
+    const bool two_streams = t_done != nullptr;
+    {
+        const int rc1 = pcr_nn_features_impl(ctx, fs, ms, ft, mt, nn_s);
+        if (t_done) {  // joined on every path: the other stream works on this call's arena
+            cudaStreamWaitEvent(ctx->stream, t_done, 0);
+            cudaEventDestroy(t_done);
+        }
+        PCR_TRY(rc1);
+    }
     PCR_ALLOC(pos, uint32_t, (size_t)ms + 1);
     uint32_t *h = (uint32_t *)ctx->pinned;
     if (mutual) {
-        PCR_ALLOC(nn_t, int, (size_t)mt);
-        PCR_TRY(pcr_nn_features_impl(ctx, ft, mt, fs, ms, nn_t));
+        if (!two_streams) PCR_TRY(pcr_nn_features_impl(ctx, ft, mt, fs, ms, nn_t));
         k_mutual_flags<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, nn_t, ms, pos);
         PCR_LAUNCHED();
         PCR_TRY(pcr_exclusive_scan_u32(ctx, pos, ms));

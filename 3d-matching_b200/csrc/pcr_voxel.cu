@@ -63,8 +63,11 @@ __global__ void __launch_bounds__(256) k_vox_finalize(const u64 *__restrict__ sc
     }
 }
 
-int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, int *m_host) {
-    *m_host = 0;
+// Enqueues the whole down-sampling of one cloud on ctx->stream WITHOUT a host synchronisation: the (rank << 32 | count)
+// total of the scan is copied to *h_total (pinned, the caller's slot); once the stream has been synchronised the number of
+// occupied voxels is *h_total >> 32.  pcr_align enqueues its two clouds on two streams and waits once.
+int pcr_voxel_enqueue(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, u64 *h_total) {
+    *h_total = 0;
     if (!(voxel > 0.0)) return pcr_fail(ctx, PCR_ERR_INVALID, "voxel_size must be > 0");
     if (n == 0) return PCR_OK;
     float lo[3], hi[3];
@@ -97,7 +100,6 @@ int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 
     k_vox_count<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, g, cell, packed);
     PCR_LAUNCHED();
     PCR_TRY(pcr_exclusive_scan_u64(ctx, packed, ncells));
-    u64 *h_total = (u64 *)ctx->pinned;
     PCR_CUDA(cudaMemcpyAsync(h_total, packed + ncells, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaMemsetAsync(sums, 0, sizeof(long long) * 3 * (size_t)n, ctx->stream));
     k_vox_accum<<<div_up(n, 256), 256, 0, ctx->stream>>>(pts, n, cell, packed, ldexp(1.0, k), sums);
@@ -107,6 +109,13 @@ int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 
     PCR_LAUNCHED();
     delete ks;
     PCR_CUDA(cudaGetLastError());
+    return PCR_OK;
+}
+
+int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 *out, int *m_host) {
+    *m_host = 0;
+    u64 *h_total = (u64 *)ctx->pinned;
+    PCR_TRY(pcr_voxel_enqueue(ctx, pts, n, voxel, out, h_total));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     *m_host = (int)(*h_total >> 32);
     return PCR_OK;
