@@ -551,24 +551,29 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
     return PCR_OK;
 }
 
-// scores [hyp_begin, hyp_end): leaves up to cap records (unsorted) in the pinned buffer; counts returned
-int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt,
-                         const int *corr, int c, double max_dist, double edge_sim, long long hyp_begin,
-                         long long hyp_end, u64 seed, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
-                         int cap, int *n_recs_host, long long *n_surv_host) {
+// One wave in two steps so that the NEXT wave's hypotheses can be generated (on another stream) while this wave's
+// survivors are validated: generation does not depend on the best result so far, validation does.
+struct WaveWork {
+    Survivor *surv;
+    unsigned char *hdr;       // 4 counters (survivors, records, ticket, -) + the record buffer
+    int *bucket_best;
+    long long hyp_begin, count;
+    int cap;
+};
+
+// step 1 (on ctx->stream, scratch from the arena — the caller releases it): survivors of [hyp_begin, hyp_end)
+static int wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, double max_dist,
+                         double edge_sim, long long hyp_begin, long long hyp_end, u64 seed, int cap, WaveWork *ww) {
     const long long count = hyp_end - hyp_begin;
-    *n_recs_host = 0;
-    *n_surv_host = 0;
-    if (count <= 0) return PCR_OK;
+    ww->hyp_begin = hyp_begin;
+    ww->count = count;
+    ww->cap = cap;
     if (count > (1LL << 30)) return pcr_fail(ctx, PCR_ERR_INVALID, "wave too large");
-    const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
     PCR_ALLOC(surv, Survivor, (size_t)count);
     // counters and records share one buffer so that the common case (few records) needs ONE D2H copy + sync
-    constexpr int FIRST = 64;
     unsigned char *hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)cap);
     if (!hdr) return PCR_ERR_OOM;
     unsigned int *counters = (unsigned int *)hdr;
-    pcr_hyp_record *recs = (pcr_hyp_record *)(hdr + 16);
     PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
     PCR_ALLOC(bucket_best, int, VAL_BUCKETS);
     PCR_CUDA(cudaMemsetAsync(bucket_best, 0xff, VAL_BUCKETS * sizeof(int), ctx->stream));
@@ -578,6 +583,28 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
                                                                        hyp_begin, count, seed, surv, counters);
         PCR_LAUNCHED();
     }
+    PCR_CUDA(cudaGetLastError());
+    ww->surv = surv;
+    ww->hdr = hdr;
+    ww->bucket_best = bucket_best;
+    return PCR_OK;
+}
+
+// step 2: validation against (best_cnt, best_sumq), records to the host (sorted by hypothesis)
+static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt, const int *corr, int c,
+                         double max_dist, const WaveWork &ww, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
+                         int *n_recs_host, long long *n_surv_host) {
+    const long long count = ww.count, hyp_begin = ww.hyp_begin, hyp_end = ww.hyp_begin + ww.count;
+    const int cap = ww.cap;
+    Survivor *surv = ww.surv;
+    unsigned char *hdr = ww.hdr;
+    unsigned int *counters = (unsigned int *)hdr;
+    pcr_hyp_record *recs = (pcr_hyp_record *)(hdr + 16);
+    int *bucket_best = ww.bucket_best;
+    constexpr int FIRST = 64;
+    *n_recs_host = 0;
+    *n_surv_host = 0;
+    if (count <= 0) return PCR_OK;
     // CTA size: the duration of a wave is bounded below by ONE full evaluation (ceil(ms / threads) sequential rounds of
     // ~8 us: 290 us for 9k points with 256 threads — measured: the waves ran at 22 % warp occupancy, waiting for such
     // tails), so larger CTAs shorten every wave; smaller CTAs prune at a finer grain and pack better.
@@ -640,8 +667,6 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     if (ctx->profiling && pend_idx < ctx->pending.size())
         ctx->pending[pend_idx].bytes = (double)hc[0] * (16.0 * ms + 16.0 * w.g.n + 8.0 * c);
     const unsigned int nrec = hc[1];
-    ctx->cur_block = mark_block;
-    ctx->cur_off = mark_off;
     if (nrec > (unsigned int)cap)
         return pcr_fail(ctx, PCR_ERR_INVALID, "ransac wave produced %u records, capacity %d", nrec, cap);
     if (nrec) {
@@ -656,6 +681,23 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     }
     *n_recs_host = (int)nrec;
     return PCR_OK;
+}
+
+// scores [hyp_begin, hyp_end): leaves up to cap records (sorted by hypothesis) in recs_host; counts returned
+int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt,
+                         const int *corr, int c, double max_dist, double edge_sim, long long hyp_begin,
+                         long long hyp_end, u64 seed, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
+                         int cap, int *n_recs_host, long long *n_surv_host) {
+    *n_recs_host = 0;
+    *n_surv_host = 0;
+    if (hyp_end - hyp_begin <= 0) return PCR_OK;
+    const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
+    WaveWork ww;
+    int rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, hyp_begin, hyp_end, seed, cap, &ww);
+    if (rc == PCR_OK) rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, ww, best_cnt, best_sumq, recs_host, n_recs_host, n_surv_host);
+    ctx->cur_block = mark_block;
+    ctx->cur_off = mark_off;
+    return rc;
 }
 
 extern "C" int pcr_ransac_scan(const pcr_hyp_record *recs, int n, int64_t hyp_begin, int64_t hyp_end, int c, int ms,
@@ -720,28 +762,84 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
     static const int wave_growth = getenv("PCR_WAVE_GROWTH") ? atoi(getenv("PCR_WAVE_GROWTH")) : 64;
     int64_t begin = 0, wave = wave_first;  // small blind first wave (no best to prune against yet), then growing to fill the GPU
     int64_t survivors = 0;
+    // The hypotheses of the SECOND wave are generated on another stream while the first wave's survivors are validated
+    // (generation needs no result of the first wave; its validation does): ~55 us of the 100k-hypothesis run leave the
+    // critical path.  Only with confidence 1.0, where the run cannot stop early and the second wave is certain to be needed:
+    // with the reference's 0.999 the first wave usually ends the run, and the discarded generation (which the call must
+    // still wait for) was measured to cost 0.04 ms per alignment.  PCR_RANSAC_SPECULATE=0: never, =2: always.
+    static const int spec_mode = getenv("PCR_RANSAC_SPECULATE") ? atoi(getenv("PCR_RANSAC_SPECULATE")) : 1;
+    const bool speculate = spec_mode == 2 || (spec_mode == 1 && confidence >= 1.0);
+    const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;
+    WaveWork spec;
+    cudaEvent_t spec_done = nullptr;
+    int wave_idx = 0;
+    int rc_all = PCR_OK;
     while (begin < max_iter && begin < res->est_k) {
         const int64_t end = std::min<int64_t>(max_iter, begin + wave);
+        const int64_t next_wave = std::min<int64_t>(wave * wave_growth, 1 << 20);
         int cap = 4096;
         int nrec = 0;
         long long nsurv = 0;
-        for (;;) {
+        recs.resize((size_t)cap);
+        int rc;
+        if (wave_idx == 0 && speculate && ctx->aux2_stream && ctx->aux2_stream != ctx->stream && end < max_iter) {
+            WaveWork w0;
+            rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, begin, end, seed, cap, &w0);
+            if (rc == PCR_OK) {
+                cudaEvent_t in_ready;
+                cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming);
+                cudaEventRecord(in_ready, ctx->stream);  // the correspondences and clouds are complete at this point of the stream
+                cudaStreamWaitEvent(ctx->aux2_stream, in_ready, 0);
+                cudaEventDestroy(in_ready);
+                cudaStream_t keep = ctx->stream;
+                ctx->stream = ctx->aux2_stream;
+                const int rcs = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, end, std::min<int64_t>(max_iter, end + next_wave), seed,
+                                              4096, &spec);
+                ctx->stream = keep;
+                if (rcs == PCR_OK && cudaEventCreateWithFlags(&spec_done, cudaEventDisableTiming) == cudaSuccess)
+                    cudaEventRecord(spec_done, ctx->aux2_stream);
+                else cudaStreamSynchronize(ctx->aux2_stream);  // no speculation: the wave is generated again in its turn
+                rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, w0, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
+            }
+        } else if (wave_idx == 1 && spec_done) {
+            cudaStreamWaitEvent(ctx->stream, spec_done, 0);
+            cudaEventDestroy(spec_done);
+            spec_done = nullptr;
+            rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, spec, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
+        } else {
+            rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, begin, end, seed, res->inlier_count,
+                                      res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
+        }
+        // a wave whose records did not fit: generation + validation again with a larger buffer
+        while (rc == PCR_ERR_INVALID && cap < (1 << 24) && (int64_t)cap < end - begin) {
+            cap *= 16;
             recs.resize((size_t)cap);
-            const int rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, begin, end, seed,
-                                                res->inlier_count, res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
-            if (rc == PCR_OK) break;
-            if (rc == PCR_ERR_INVALID && cap < (1 << 24) && (int64_t)cap < end - begin) { cap *= 16; continue; }
-            return rc;
+            rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, begin, end, seed, res->inlier_count,
+                                      res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
+        }
+        if (rc != PCR_OK) {
+            rc_all = rc;
+            break;
+        }
+        if (wave_idx >= 1 && !spec_done) {  // the scratch of the first two waves is released once both are done
+            ctx->cur_block = mark_block;
+            ctx->cur_off = mark_off;
         }
         survivors += nsurv;
         int stop = 0;
         pcr_ransac_scan(recs.data(), nrec, begin, end, c, ms, confidence, w.k_d, res, &stop);
         begin = end;
+        wave_idx++;
         if (stop) break;
         // completed evaluations are shared inside a wave (bucket_best), so the second wave can be large: measured
         // (2048, x8) 1.22 ms, (2048, x64) 1.09 ms, (4096, x64) 1.12 ms, (1024, x128) 1.07 ms for 100k hypotheses
-        wave = std::min<int64_t>(wave * wave_growth, 1 << 20);
+        wave = next_wave;
     }
+    if (spec_done) {  // a speculated wave that is not needed (early stop, error): its kernels still use this call's arena
+        cudaStreamWaitEvent(ctx->stream, spec_done, 0);
+        cudaEventDestroy(spec_done);
+    }
+    if (rc_all != PCR_OK) return rc_all;
     res->survivors = survivors;
     res->k_d = w.k_d;
     if (res->hyp_evaluated > max_iter) res->hyp_evaluated = max_iter;

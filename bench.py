@@ -361,7 +361,11 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
-ISSUE_BOUND = ("ransac_validate", "ransac_generate", "knn_cov", "knn_list")  # working set in L1/L2, DRAM traffic ~ 0
+# working set in L1/L2, DRAM traffic far below the algorithmic bytes; icp_pass: the per-point state of a certified
+# pass is L2-resident (ncu: 1.9 MB of DRAM traffic per pass against 5.2 MB algorithmic at 100k points) and the pass is a
+# chain of dependent latencies + instruction issue, so the HBM figure (the north star's target form) is kept as a
+# secondary field ("report the ICP roofline with the bound that actually binds")
+ISSUE_BOUND = ("ransac_validate", "ransac_generate", "knn_cov", "knn_list", "icp_pass")
 
 
 def roofline_of(name, st, peaks, clk):
@@ -380,6 +384,12 @@ def roofline_of(name, st, peaks, clk):
         roof = {"kernel": name, "bound": "issue", "achieved": ach, "peak": peak, "unit": "Gthread-inst/s", "frac": ach / peak,
                 "l2_level_algorithmic_gbs": st["bytes"] / secs / 1e9,
                 "note": "thread instructions per launch: smsp__thread_inst_executed.sum of the committed ncu capture; time: live CUDA events"}
+        if name == "icp_pass":
+            roof.update({"hbm_algorithmic_gbs": st["bytes"] / secs / 1e9, "hbm_frac": st["bytes"] / secs / 1e9 / peaks["hbm_gbs"],
+                         "issue_active_pct_ncu": ncu_field(name, "issue_active_pct"),
+                         "note": "a launch = one ICP pass (the persistent kernel's time divided by the passes it ran); thread instructions "
+                                 "per pass from the committed 51-pass ncu capture (tools/prof_icp.py), time from live CUDA events; "
+                                 "hbm_* = 52 B per point and pass against the measured HBM peak (the north star's form)"})
     else:
         ach = st["bytes"] / secs / 1e9
         roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
@@ -537,7 +547,7 @@ def ncu_traffic(kernel_class):
                 t = json.load(f)
             e = t["kernels"].get(kernel_class)
             if e:
-                return e["dram_bytes_per_launch"], f"profiles/{fn} ({t['source']})"
+                return e["dram_bytes_per_launch"], f"profiles/{fn} ({e.get('source') or t['source']})"
         except (OSError, ValueError, KeyError):
             pass
     return None, None
@@ -681,6 +691,11 @@ def run_aux(eng, args, world, rank, peaks):
         gbs = ks["bytes"] / (ks["ms"] * 1e-3) / 1e9
         icp.update({"pass_kernel_us": us, "pass_kernel_gbs_algorithmic_52B_per_point": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
                     "kernel_iters_per_s_per_gpu": 1e6 / us})
+        ti = ncu_field("icp_pass_1m", "thread_inst_per_launch")
+        if ti and n == 1000000:  # the bound that binds: thread-instruction issue (148 SMs x 128 lanes x 1.965 GHz)
+            icp.update({"issue_gthread_inst_per_s": ti / us / 1e3, "frac_of_issue_peak": ti / us / 1e3 / (148 * 128 * 1.965),
+                        "issue_active_pct_ncu": ncu_field("icp_pass_1m", "issue_active_pct"),
+                        "dram_bytes_per_pass_ncu": ncu_field("icp_pass_1m", "dram_bytes_per_launch")})
     # cfg3 parity: the first 10 iterations of the same 1M-point run against the CPU oracle (src/matcher/icp.py:42-48):
     # every correspondence index, the inlier count, the fixed-point sum of d2, every bit of T
     if rank == 0 and not args.no_cpu:

@@ -275,6 +275,23 @@ def test_icp_certified_passes_ties_and_drift(orc, eng, pair):
     assert 0.2 < g.fitness < 1.0
 
 
+@pytest.mark.parametrize("cert_pass", ["0", "1", "5"])
+def test_icp_certificate_start_pass_cannot_change_a_result(orc, eng, pair, cert_pass, monkeypatch):
+    """The certificates (squared-form test, pair tier, "still none") only decide between reuse and search.  Starting them
+    at pass 0 (weak certificates of a cloud that still moves: most points take the pair tier or search again), at pass 1
+    or only at pass 5 must reproduce the oracle — which searches in every pass — bit for bit (the switch is read per call)."""
+    monkeypatch.setenv("PCR_ICP_CERT_PASS", cert_pass)
+    v = pair["v"]
+    otn = orc.estimate_normals(pair["tgt"], 2 * v, 30)
+    pert = np.eye(4); pert[:3, :3] = synth.euler_zyx(0.006, -0.004, 0.003); pert[:3, 3] = [6e-4, -5e-4, 4e-4]
+    init = pert @ pair["T"]
+    g, corr = eng.icp_point_to_plane(pair["ds"], pair["dt"], eng.pack(otn), 0.4 * v, init, 25, 0.0, 0.0)
+    o = orc.icp_point_to_plane(pair["src"], pair["tgt"], otn, 0.4 * v, init, 25, 0.0, 0.0)
+    assert np.array_equal(corr.cpu().numpy(), o.correspondence)
+    assert (g.inlier_count, g.sum_d2_fixed, g.iterations) == (o.inlier_count, o.sum_d2_fixed, o.iterations)
+    assert np.array_equal(g.transformation, o.transformation)
+
+
 @pytest.mark.parametrize("ns", [1, 2, 31, 129, 257, 1000])
 def test_icp_small_and_ragged_sizes(orc, eng, pair, ns):
     """Source sizes around the kernel's granularities (128-row groups, 256-thread CTAs), down to a single point."""

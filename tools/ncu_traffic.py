@@ -44,11 +44,16 @@ for c, ls in acc.items():
     if c == "icp_pass":
         # largest launch = the 1M-point run (21 passes), the others the 100k alignments (5 passes)
         big = max(ls, key=lambda e: e["dram_bytes"])
-        res["kernels"]["icp_pass_1m"] = {"dram_bytes_per_launch": big["dram_bytes"] / 21.0, "passes_in_capture": 21, "launches": 1}
+        res["kernels"]["icp_pass_1m"] = {"dram_bytes_per_launch": big["dram_bytes"] / 21.0, "passes_in_capture": 21, "launches": 1,
+                                         "thread_inst_per_launch": big["thread_inst"] / 21.0 if big["thread_inst"] else None,
+                                         "avg_us_under_ncu": big["us"] / 21.0}
         small = [e for e in ls if e is not big]
         if small:
+            ti = [e["thread_inst"] for e in small if e["thread_inst"] is not None]
             res["kernels"][c] = {"dram_bytes_per_launch": sum(e["dram_bytes"] for e in small) / len(small) / 5.0,
-                                 "passes_in_capture": 5, "launches": len(small)}
+                                 "passes_in_capture": 5, "launches": len(small),
+                                 "thread_inst_per_launch": (sum(ti) / len(ti) / 5.0) if ti else None,
+                                 "avg_us_under_ncu": sum(e["us"] for e in small) / len(small) / 5.0}
     else:
         ti = [e["thread_inst"] for e in ls if e["thread_inst"] is not None]
         res["kernels"][c] = {"dram_bytes_per_launch": sum(e["dram_bytes"] for e in ls) / len(ls), "launches": len(ls),
