@@ -56,8 +56,35 @@ def test_voxel_edge_cases(orc, eng):
     assert np.array_equal(xyz(eng.voxel_downsample(eng.pack(dup), 0.3)), orc.voxel_downsample(dup, 0.3))
     one = np.array([[1.5, -2.0, 3.25]], np.float32)
     assert np.array_equal(xyz(eng.voxel_downsample(eng.pack(one), 0.3)), one)
-    with pytest.raises(ValueError):  # dense voxel grid budget (PCR_ERR_TOO_LARGE)
-        eng.voxel_downsample(eng.pack(np.array([[0, 0, 0], [1e3, 1e3, 1e3]], np.float32)), 1e-3)
+    # 10^18 voxel ids: far beyond the dense table, down-sampled through the sorted-key path like any other cloud
+    far = np.array([[0, 0, 0], [1e3, 1e3, 1e3], [1e3, 1e3, 1e3]], np.float32)
+    assert np.array_equal(xyz(eng.voxel_downsample(eng.pack(far), 1e-3)), orc.voxel_downsample(far, 1e-3))
+    with pytest.raises(ValueError):  # a dimension beyond int32 (PCR_ERR_TOO_LARGE), as the oracle refuses it
+        eng.voxel_downsample(eng.pack(far), 1e-7)
+
+
+@pytest.mark.parametrize("voxel", [0.3, 0.011])
+def test_voxel_grid_beyond_the_dense_budget(orc, eng, pair, voxel):
+    """a 200-unit scene at the reference's default voxel 0.3, or a lidar sweep at 5 cm, has more voxel ids than the
+    dense table may hold (2^27).  Two dense clusters 10^5 units apart and a sprinkle of isolated points: the sorted-key
+    path must give the oracle's points bit for bit, in ascending voxel id — voxels with hundreds of points and with one."""
+    rng = np.random.default_rng(5)
+    big = voxel > 0.1
+    a = pair["src"].astype(np.float32) * (60.0 if big else 1.0)
+    b = a[: len(a) // 2] + np.array([1e5, -3e4, 2e4] if big else [2e3, -5e2, 3e2], np.float32)
+    lone = rng.uniform(-5e4, 5e4, (3000, 3)).astype(np.float32) * (1.0 if big else 0.02)
+    pts = np.concatenate([a, b, lone]).astype(np.float32)
+    rng.shuffle(pts)
+    ext = pts.max(0).astype(np.float64) - pts.min(0)
+    assert 2.0 ** 27 < np.prod(np.floor(ext / voxel) + 1) < 9.0e18
+    got = xyz(eng.voxel_downsample(eng.pack(pts), voxel))
+    want = orc.voxel_downsample(pts, voxel)
+    assert got.shape == want.shape and len(want) < len(pts) - 1000
+    assert np.array_equal(got, want)
+    # and the rest of Ply._preprocess runs on it (the search grids enlarge their cells to fit): normals + FPFH = the oracle's
+    d = eng.voxel_downsample(eng.pack(pts), voxel)
+    n = eng.estimate_normals(d, 2 * voxel, 30)
+    assert np.array_equal(xyz(n), orc.estimate_normals(want, 2 * voxel, 30))
 
 
 @pytest.mark.parametrize("radius_v,k", [(2, 30), (5, 100), (1.2, 4), (8, 256)])
