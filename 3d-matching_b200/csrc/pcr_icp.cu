@@ -721,7 +721,9 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     int &occ = ctx->occ_icp;
     if (!occ) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp_persist, ICP_THREADS, 0));
     if (occ < 1) return pcr_fail(ctx, PCR_ERR_CUDA, "k_icp_persist does not fit on an SM");
-    const int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * occ);
+    int blocks = min(div_up(ns, ICP_THREADS), ctx->sm_count * occ);
+    // diagnostic: a small grid gives a small cloud the many-chunks-per-CTA shape of a large one (tests/test_gpu_parity.py)
+    if (getenv("PCR_ICP_MAX_CTAS")) blocks = max(1, min(blocks, atoi(getenv("PCR_ICP_MAX_CTAS"))));
     const size_t pend_idx = ctx->pending.size();
     {
         // ONE launch runs all passes; the per-pass figure (52 B per point) is what the kernel statistics report,

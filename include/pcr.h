@@ -41,7 +41,8 @@ typedef enum pcr_status {
     PCR_ERR_CUDA = -2,    /* CUDA runtime failure (RuntimeError) */
     PCR_ERR_OOM = -3,     /* device allocation failed (MemoryError) */
     PCR_ERR_BUSY = -4,    /* context used concurrently */
-    PCR_ERR_TOO_LARGE = -5, /* voxel/search grid would exceed the dense-grid cell budget */
+    PCR_ERR_TOO_LARGE = -5, /* a voxel grid dimension beyond int32 or more than 2^63 voxel ids (grids beyond the dense-table
+                               budget are down-sampled through sorted 64-bit keys; search grids enlarge their cells) */
     PCR_ERR_IO = -6         /* pcr_ply_*: file missing / unreadable / short write (OSError) */
 } pcr_status;
 

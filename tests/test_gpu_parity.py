@@ -319,6 +319,25 @@ def test_icp_certificate_start_pass_cannot_change_a_result(orc, eng, pair, cert_
     assert np.array_equal(g.transformation, o.transformation)
 
 
+@pytest.mark.parametrize("ctas", ["8", "3", "1"])
+def test_icp_many_chunks_per_cta(orc, eng, pair, ctas, monkeypatch):
+    """A small grid (PCR_ICP_MAX_CTAS) gives a 20k-point cloud the many-chunks-per-CTA shape of a 1M-point one (double-buffered
+    row staging, per-group barriers, a thread owning several points): every correspondence, sum and bit of the transform
+    must equal the oracle's, with a partial last chunk too."""
+    monkeypatch.setenv("PCR_ICP_MAX_CTAS", ctas)
+    v = pair["v"]
+    otn = orc.estimate_normals(pair["tgt"], 2 * v, 30)
+    pert = np.eye(4); pert[:3, :3] = synth.euler_zyx(0.004, -0.003, 0.002); pert[:3, 3] = [4e-4, -3e-4, 2e-4]
+    init = pert @ pair["T"]
+    for cut in (0, 77):
+        src = pair["src"][: len(pair["src"]) - cut]
+        g, corr = eng.icp_point_to_plane(eng.pack(src), pair["dt"], eng.pack(otn), 0.4 * v, init, 20, 0.0, 0.0)
+        o = orc.icp_point_to_plane(src, pair["tgt"], otn, 0.4 * v, init, 20, 0.0, 0.0)
+        assert np.array_equal(corr.cpu().numpy(), o.correspondence)
+        assert (g.inlier_count, g.sum_d2_fixed, g.iterations) == (o.inlier_count, o.sum_d2_fixed, o.iterations)
+        assert np.array_equal(g.transformation, o.transformation)
+
+
 @pytest.mark.parametrize("ns", [1, 2, 31, 129, 257, 1000])
 def test_icp_small_and_ragged_sizes(orc, eng, pair, ns):
     """Source sizes around the kernel's granularities (128-row groups, 256-thread CTAs), down to a single point."""
