@@ -403,108 +403,6 @@ __global__ void __launch_bounds__(VAL_THREADS) k_ransac_validate(
     }
 }
 
-// ---- small blind first wave ------------------------------------------------------------------------------------------
-// The first wave of a run has no best result to prune against, and while it is small (2,048 hypotheses, 50-100 survivors)
-// its survivors all start together, so nothing completes early enough to be shared either: the wave lasts exactly one full
-// evaluation — ceil(M_s / 1024) sequential rounds of one CTA — on a third of the SMs.  Here a survivor is cut into PARTS
-// interleaved sets of 1,024-point chunks, handed out as (survivor, part) tickets; the parts add their count and fixed-point
-// sum (integers: any order) to the survivor's totals and the part that arrives last emits the record.  No pruning, hence
-// no order dependence; every survivor with a non-empty inlier set is reported and the host replay (pcr_ransac_scan) picks
-// the prefix maxima, exactly as from the records of the general kernel.
-template <bool LISTS>
-__global__ void __launch_bounds__(1024) k_ransac_validate_blind(
-    const float4 *__restrict__ src, const float4 *__restrict__ src_orig, int ms, const float4 *__restrict__ tgt, Grid g,
-    const int2 *__restrict__ corr, int c, double max_dist, float r2, double sc_d, Survivor *__restrict__ surv,
-    const unsigned int *__restrict__ n_surv, long long best_cnt, long long best_sumq, pcr_hyp_record *__restrict__ recs,
-    unsigned int *__restrict__ n_recs, unsigned int rec_cap, unsigned int *__restrict__ next_ticket,
-    unsigned int *__restrict__ part_done, int parts, CellLists L) {
-    __shared__ double sT[12];
-    __shared__ long long red[32][3];
-    __shared__ long long s_tot[2];
-    __shared__ unsigned int s_next;
-    __shared__ int s_last;
-    const unsigned int ns = *n_surv;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nchunks = (ms + 1023) / 1024;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_next = atomicAdd(next_ticket, 1u);
-        __syncthreads();
-        const unsigned int sidx = s_next / (unsigned int)parts;
-        const int part = (int)(s_next % (unsigned int)parts);
-        if (sidx >= ns) break;
-        if (threadIdx.x < 12) sT[threadIdx.x] = surv[sidx].T[threadIdx.x];
-        __syncthreads();
-        const double *T = sT;
-        long long cnt = 0, sumq = 0;
-        for (int kc = part; kc < nchunks; kc += parts) {
-            const int i = kc * 1024 + threadIdx.x;
-            if (i < ms) {
-                const float4 p = __ldg(src + i);
-                const float3 q = xform_pt(T, p.x, p.y, p.z);
-                float d2;
-                if ((LISTS ? lists_nn1(L, g, q.x, q.y, q.z, r2, &d2) : grid_nn1(g, q.x, q.y, q.z, r2, &d2)) >= 0) {
-                    cnt++;
-                    sumq += fixed_ll((double)d2, sc_d);
-                }
-            }
-        }
-        cnt = warp_sum_ll(cnt);
-        sumq = warp_sum_ll(sumq);
-        if (lane == 0) { red[warp][0] = cnt; red[warp][1] = sumq; }
-        __syncthreads();
-        if (warp == 0) {
-            long long a = red[lane][0], b = red[lane][1];
-            a = warp_sum_ll(a);
-            b = warp_sum_ll(b);
-            if (lane == 0) {
-                atomicAdd((u64 *)&surv[sidx].f_cnt, (u64)a);
-                atomicAdd((u64 *)&surv[sidx].f_sumq, (u64)b);
-                __threadfence();
-                const unsigned int prev = atomicAdd(part_done + sidx, 1u);
-                const int last = prev == (unsigned int)parts - 1u;
-                if (last) {
-                    __threadfence();
-                    s_tot[0] = (long long)atomicAdd((u64 *)&surv[sidx].f_cnt, 0ull);
-                    s_tot[1] = (long long)atomicAdd((u64 *)&surv[sidx].f_sumq, 0ull);
-                }
-                s_last = last;
-            }
-        }
-        __syncthreads();
-        if (!s_last) continue;  // block-uniform
-        const long long a = s_tot[0], b = s_tot[1];
-        if (!ransac_better(a, b, best_cnt, best_sumq)) continue;
-        long long cin = 0;
-        for (int i = threadIdx.x; i < c; i += 1024) {
-            const int2 cc = __ldg(corr + i);
-            const float4 p = __ldg(src_orig + cc.x), q = __ldg(tgt + cc.y);
-            const double x = p.x, y = p.y, z = p.z;
-            const double dx = (((T[0] * x + T[1] * y) + T[2] * z) + T[3]) - (double)q.x;
-            const double dy = (((T[4] * x + T[5] * y) + T[6] * z) + T[7]) - (double)q.y;
-            const double dz = (((T[8] * x + T[9] * y) + T[10] * z) + T[11]) - (double)q.z;
-            if (sqrt((dx * dx + dy * dy) + dz * dz) < max_dist) cin++;
-        }
-        cin = warp_sum_ll(cin);
-        if (lane == 0) red[warp][2] = cin;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long d = 0;
-            for (int w2 = 0; w2 < 32; w2++) d += red[w2][2];
-            const unsigned int slot = atomicAdd(n_recs, 1u);
-            if (slot < rec_cap) {
-                pcr_hyp_record *o = recs + slot;
-                o->hyp = surv[sidx].hyp;
-                o->inlier_count = a;
-                o->sum_d2_fixed = b;
-                o->corr_inliers = (int)d;
-                o->reserved = 0;
-                for (int i = 0; i < 12; i++) o->transformation[i] = sT[i];
-            }
-        }
-    }
-}
-
 // ---- manual-step twins -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_ransac_step(const float4 *__restrict__ src, const float4 *__restrict__ tgt,
                                                      const int2 *__restrict__ corr, int c, u64 seed, long long h_begin,
@@ -655,34 +553,23 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
 
 // One wave in two steps so that the NEXT wave's hypotheses can be generated (on another stream) while this wave's
 // survivors are validated: generation does not depend on the best result so far, validation does.
-constexpr long long BLIND_SPLIT_MAX = 4096;  // hypotheses of a blind wave that is still evaluated part-wise (see k_ransac_validate_blind)
-
 struct WaveWork {
     Survivor *surv;
     unsigned char *hdr;       // 4 counters (survivors, records, ticket, -) + the record buffer
     int *bucket_best;
-    unsigned int *part_done;  // small blind wave only: parts of each survivor that have been added (else nullptr)
     long long hyp_begin, count;
     int cap;
 };
 
 // step 1 (on ctx->stream, scratch from the arena — the caller releases it): survivors of [hyp_begin, hyp_end)
 static int wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, double max_dist,
-                         double edge_sim, long long hyp_begin, long long hyp_end, u64 seed, int cap, WaveWork *ww, bool blind = false) {
+                         double edge_sim, long long hyp_begin, long long hyp_end, u64 seed, int cap, WaveWork *ww) {
     const long long count = hyp_end - hyp_begin;
     ww->hyp_begin = hyp_begin;
     ww->count = count;
     ww->cap = cap;
     if (count > (1LL << 30)) return pcr_fail(ctx, PCR_ERR_INVALID, "wave too large");
     PCR_ALLOC(surv, Survivor, (size_t)count);
-    ww->part_done = nullptr;
-    static const int blind_parts = getenv("PCR_BLIND_PARTS") ? atoi(getenv("PCR_BLIND_PARTS")) : 4;
-    if (blind && blind_parts > 1 && count <= BLIND_SPLIT_MAX && cap >= count) {  // k_ransac_validate_blind: totals start at zero, every survivor may report
-        PCR_ALLOC(pd, unsigned int, (size_t)count);
-        PCR_CUDA(cudaMemsetAsync(pd, 0, sizeof(unsigned int) * (size_t)count, ctx->stream));
-        PCR_CUDA(cudaMemsetAsync(surv, 0, sizeof(Survivor) * (size_t)count, ctx->stream));
-        ww->part_done = pd;
-    }
     // counters and records share one buffer so that the common case (few records) needs ONE D2H copy + sync
     unsigned char *hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)cap);
     if (!hdr) return PCR_ERR_OOM;
@@ -743,21 +630,7 @@ static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
         cudaEventCreate(&dbg_b);
         cudaEventRecord(dbg_a, ctx->stream);
     }
-    if (ww.part_done && blind) {
-        static const int blind_parts = getenv("PCR_BLIND_PARTS") ? atoi(getenv("PCR_BLIND_PARTS")) : 4;
-        const int parts = std::max(2, std::min(blind_parts, nchunks));
-        const int bblocks = (int)std::min<long long>(count * parts, (long long)ctx->sm_count);
-        KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
-        if (w.use_lists)
-            k_ransac_validate_blind<true><<<bblocks, 1024, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist, w.r2,
-                                                                            ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, recs, counters + 1,
-                                                                            (unsigned int)cap, counters + 2, ww.part_done, parts, w.cl);
-        else
-            k_ransac_validate_blind<false><<<bblocks, 1024, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist, w.r2,
-                                                                             ldexp(1.0, w.k_d), surv, counters, best_cnt, best_sumq, recs, counters + 1,
-                                                                             (unsigned int)cap, counters + 2, ww.part_done, parts, w.cl);
-        PCR_LAUNCHED();
-    } else {
+    {
         KScope ks(ctx, KC_RANSAC_VALIDATE, 0.0);
 #define PCR_VAL_LAUNCH(NT, LS)                                                                                                   \
         k_ransac_validate<NT, LS><<<vblocks, NT, 0, ctx->stream>>>(w.src_sorted, src, ms, tgt, w.g, (const int2 *)corr, c, max_dist,  \
@@ -820,7 +693,7 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     if (hyp_end - hyp_begin <= 0) return PCR_OK;
     const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
     WaveWork ww;
-    int rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, hyp_begin, hyp_end, seed, cap, &ww, best_cnt <= 0);
+    int rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, hyp_begin, hyp_end, seed, cap, &ww);
     if (rc == PCR_OK) rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, ww, best_cnt, best_sumq, recs_host, n_recs_host, n_surv_host);
     ctx->cur_block = mark_block;
     ctx->cur_off = mark_off;
@@ -911,7 +784,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
         int rc;
         if (wave_idx == 0 && speculate && ctx->aux2_stream && ctx->aux2_stream != ctx->stream && end < max_iter) {
             WaveWork w0;
-            rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, begin, end, seed, cap, &w0, res->inlier_count <= 0);
+            rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, begin, end, seed, cap, &w0);
             if (rc == PCR_OK) {
                 cudaEvent_t in_ready;
                 cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming);
