@@ -277,7 +277,7 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
         bool on;
         ~StreamSwap() {
             if (on) {
-                cudaStreamSynchronize(c->stream);
+                pcr_sync_stream(c, c->stream);
                 c->stream = saved;
             }
         }
@@ -332,10 +332,10 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
             if (two) ctx->stream = ctx->aux_stream;
             rc = preprocess_voxel_enqueue(ctx, tgt, nt, v, &td, &h_tot[1]);
             ctx->stream = keep;
-            if (two && cudaStreamSynchronize(ctx->aux_stream) != cudaSuccess && rc == PCR_OK)
+            if (two && pcr_sync_stream(ctx, ctx->aux_stream) != cudaSuccess && rc == PCR_OK)
                 rc = pcr_fail(ctx, PCR_ERR_CUDA, "voxel grid (auxiliary stream): %s", cudaGetErrorString(cudaGetLastError()));
         }
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == PCR_OK)
+        if (pcr_sync_stream(ctx, ctx->stream) != cudaSuccess && rc == PCR_OK)
             rc = pcr_fail(ctx, PCR_ERR_CUDA, "voxel grid: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc == PCR_OK) {
             ms = (int)(h_tot[0] >> 32);
@@ -417,7 +417,7 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
             const int r = full_normals(h);
             if (phase->load(std::memory_order_acquire) == 0) phase->store(2, std::memory_order_release);
             if (r != PCR_OK) return r;
-            return cudaStreamSynchronize(h->stream) == cudaSuccess ? PCR_OK : PCR_ERR_CUDA;
+            return pcr_sync_stream(h, h->stream) == cudaSuccess ? PCR_OK : PCR_ERR_CUDA;
         });
     }
     // the helper's job refers to locals of this call: it is joined on EVERY return path
@@ -500,7 +500,7 @@ static int align_device(pcr_ctx *ctx, const float4 *src, int ns, const float4 *t
     }
     if (ready) cudaEventDestroy(ready);
     if (rc != PCR_OK) return rc;
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
     res->n_src_down = ms;
     res->n_tgt_down = mt;
     res->n_corr = c;

@@ -146,6 +146,11 @@ struct pcr_ctx {
     void *dist = nullptr;              // multi-GPU state (pcr_dist.cu): NCCL communicator, exchange buffers, worker contexts
     cudaStream_t hp_stream = nullptr;  // highest-priority stream: pcr_align's critical path runs here while the helper works
     cudaStream_t aux_stream = nullptr; // second highest-priority stream: work pcr_align issues next to its critical path
+    // Host waits: spinning cudaStreamSynchronize by default (lowest latency for one alignment at a time).  pcr_align_batch
+    // switches its worker contexts to a blocking event wait when there are more host threads than cores (several ranks x
+    // workers x helper threads on one box): spinning threads then only steal the cores the launching threads need.
+    bool blocking_sync = false;
+    cudaEvent_t sync_ev = nullptr;
     cudaStream_t aux2_stream = nullptr; // third: the target -> source direction of the descriptor matching (pcr_match.cu)
 };
 
@@ -176,6 +181,8 @@ struct KScope {
     ~KScope();
     void set_launches(long long n) { p.launches = n; }
 };
+
+cudaError_t pcr_sync_stream(pcr_ctx *ctx, cudaStream_t s);  // cudaStreamSynchronize, or a blocking event wait (ctx->blocking_sync)
 
 // ---- error handling -------------------------------------------------------------------------------
 int pcr_fail(pcr_ctx *ctx, int code, const char *fmt, ...);

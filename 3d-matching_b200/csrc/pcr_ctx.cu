@@ -142,6 +142,17 @@ int Worker::wait() {
     return rc;
 }
 
+cudaError_t pcr_sync_stream(pcr_ctx *ctx, cudaStream_t s) {
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(s);
+    if (!ctx->sync_ev && cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->sync_ev = nullptr;
+        return cudaStreamSynchronize(s);
+    }
+    const cudaError_t e = cudaEventRecord(ctx->sync_ev, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->sync_ev);
+}
+
 // helper context of `ctx` (created on first use): same device, own non-blocking stream
 int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
     if (!ctx->helper) {
@@ -172,6 +183,7 @@ int pcr_helper_get(pcr_ctx *ctx, pcr_ctx **out) {
         ctx->worker = new Worker();
     }
     ctx->helper->profiling = ctx->profiling;
+    ctx->helper->blocking_sync = ctx->blocking_sync;
     *out = ctx->helper;
     return PCR_OK;
 }
@@ -230,6 +242,7 @@ int pcr_destroy(pcr_ctx *ctx) {
     if (ctx->hp_stream) cudaStreamDestroy(ctx->hp_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     delete ctx;
     return PCR_OK;
 }

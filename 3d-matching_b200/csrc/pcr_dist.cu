@@ -21,6 +21,8 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+
 #include "pcr_common.cuh"
 
 typedef unsigned long long u64;
@@ -346,6 +348,32 @@ int pcr_align_batch(pcr_ctx *ctx, int n_local, const float *const *src_dev, cons
         d->workers.push_back(wctx);
     }
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));  // the inputs were produced on the caller's stream
+    // Host waits of the workers: every alignment waits ~7 times for the GPU, and a spinning wait holds a core.  With one rank
+    // per GPU, `workers` contexts per rank and a helper thread per context there can be more host threads than cores (8 ranks
+    // x 6 workers x 2 on a 32-core box): the threads then block on an event instead (PCR_BATCH_BLOCKING=0/1 overrides).
+    {
+        static const int bl_env = getenv("PCR_BATCH_BLOCKING") ? atoi(getenv("PCR_BATCH_BLOCKING")) : -1;
+        cpu_set_t set;
+        int cores = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        if (cores < 1) cores = 1;
+        // measured on one B200 with the affinity cut to 2 / 4 / 16 cores (tools/gpu_batch_workers.py, 6 workers = 12 threads):
+        // spinning 1,238 / 1,513 / 1,734 pairs/s, blocking 1,615 / 1,620 / 1,678 — and 1,256 -> 534 with a single worker,
+        // so blocking only when the threads outnumber the cores at least two to one
+        const bool blocking = bl_env >= 0 ? bl_env != 0 : (long long)world * workers * 2 >= 2LL * cores;
+        ctx->blocking_sync = blocking;
+        if (ctx->helper) ctx->helper->blocking_sync = blocking;
+        for (pcr_ctx *wc : d->workers) {
+            wc->blocking_sync = blocking;
+            if (wc->helper) wc->helper->blocking_sync = blocking;
+        }
+    }
+    struct SyncRestore {  // single alignments on this context spin again
+        pcr_ctx *c;
+        ~SyncRestore() {
+            c->blocking_sync = false;
+            if (c->helper) c->helper->blocking_sync = false;
+        }
+    } sync_restore{ctx};
     std::vector<double> mine((size_t)per * 18, 0.0);
     std::vector<int> rcs((size_t)workers, PCR_OK);
     auto work = [&](int wi) {

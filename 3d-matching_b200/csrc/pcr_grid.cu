@@ -115,7 +115,7 @@ int pcr_bounds_pair(pcr_ctx *ctx, const float4 *pa, int na, const float4 *pb, in
     }
     float *hb = (float *)ctx->pinned;
     PCR_CUDA(cudaMemcpyAsync(hb, out, 12 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
     for (int cloud = 0; cloud < (nb > 0 ? 2 : 1); cloud++) {
         pcr_ctx::BoundsEntry e;
         e.ptr = cloud ? (const void *)pb : (const void *)pa;

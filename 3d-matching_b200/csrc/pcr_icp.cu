@@ -737,7 +737,7 @@ int pcr_icp_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, con
     PCR_CUDA(cudaGetLastError());
     PCR_CUDA(cudaMemcpyAsync(hS, dS, state_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (sync_result) {
-        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
         for (int i = 0; i < 16; i++) res->transformation[i] = hS->T_out[i];
         res->fitness = hS->fitness;
         res->inlier_rmse = hS->rmse;

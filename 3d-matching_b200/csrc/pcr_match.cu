@@ -138,7 +138,7 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
         k_corr_compact<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, pos, ms, corr);
         PCR_LAUNCHED();
         PCR_CUDA(cudaMemcpyAsync(h, pos + ms, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
         const int c = (int)*h;
         // Open3D: int(corres_mutual.size()) >= int(mutual_consistency_ratio * num_src) — both sides truncated (A.5)
         if (c >= (int)(mutual_ratio * (double)ms)) {
@@ -153,7 +153,7 @@ int pcr_match_impl(pcr_ctx *ctx, const float *fs, int ms, const float *ft, int m
     k_corr_compact<<<div_up(ms, 256), 256, 0, ctx->stream>>>(nn_s, pos, ms, corr);
     PCR_LAUNCHED();
     PCR_CUDA(cudaMemcpyAsync(h, pos + ms, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
     *c_host = (int)*h;
     return PCR_OK;
 }

@@ -652,7 +652,7 @@ static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     unsigned char *hp = (unsigned char *)ctx->pinned;
     const int first = cap < FIRST ? cap : FIRST;
     PCR_CUDA(cudaMemcpyAsync(hp, hdr, 16 + sizeof(pcr_hyp_record) * (size_t)first, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
     const unsigned int *hc = (const unsigned int *)hp;
     *n_surv_host = hc[0];
     if (dbg) {
@@ -675,7 +675,7 @@ static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
         if (nrec > got) {
             PCR_CUDA(cudaMemcpyAsync(recs_host + got, recs + got, sizeof(pcr_hyp_record) * (nrec - got), cudaMemcpyDeviceToHost,
                                      ctx->stream));
-            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+            PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
         }
         std::sort(recs_host, recs_host + nrec, [](const pcr_hyp_record &a, const pcr_hyp_record &b) { return a.hyp < b.hyp; });
     }

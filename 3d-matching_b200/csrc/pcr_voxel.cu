@@ -214,7 +214,7 @@ int pcr_voxel_impl(pcr_ctx *ctx, const float4 *pts, int n, double voxel, float4 
     *m_host = 0;
     u64 *h_total = (u64 *)ctx->pinned;
     PCR_TRY(pcr_voxel_enqueue(ctx, pts, n, voxel, out, h_total));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(pcr_sync_stream(ctx, ctx->stream));
     *m_host = (int)(*h_total >> 32);
     return PCR_OK;
 }

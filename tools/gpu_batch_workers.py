@@ -3,6 +3,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "3d-matching_b200"))
 import numpy as np, torch
+if os.environ.get("CORES"):  # emulate a box with fewer cores than host threads (several ranks sharing the CPUs)
+    os.sched_setaffinity(0, set(range(int(os.environ["CORES"]))))
 from pcr_b200 import synth
 from pcr_b200.engine import get_engine
 eng = get_engine(0); eng.comm_init()
@@ -15,7 +17,7 @@ for i in range(B):
 p = eng.default_params(v); p.ransac_max_iter = 100000; p.seed = 7
 print("host cores", len(os.sched_getaffinity(0)))
 ref = None
-for w in (1, 2, 3, 4, 6, 8):
+for w in [int(x) for x in os.environ.get("WORKERS", "1,2,3,4,6,8").split(",")]:
     eng.align_batch(pairs, p, B, workers=w)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     tab = eng.align_batch(pairs, p, B, workers=w)
