@@ -70,12 +70,11 @@ int pcr_nn_features_tc_impl(pcr_ctx *ctx, const float *fq, int nq, const float *
 
 // PCR_MATCH_EXACT=1 forces the CUDA-core exact kernel for every size (bring-up / A-B comparison aid)
 static bool match_use_tensor_cores() {
-    static int v = -1;
-    if (v < 0) {
+    static const bool v = [] {  // initialised once, thread-safely
         const char *e = getenv("PCR_MATCH_EXACT");
-        v = (e && e[0] == '1') ? 0 : 1;
-    }
-    return v == 1;
+        return !(e && e[0] == '1');
+    }();
+    return v;
 }
 
 int pcr_nn_features_impl(pcr_ctx *ctx, const float *fq, int nq, const float *fb, int nb, int *nn) {

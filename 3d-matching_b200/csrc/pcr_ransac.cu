@@ -617,9 +617,9 @@ static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     int stride = (int)(nchunks * 0.618);  // stride coprime with the chunk count (1 when there are < 3 chunks)
     if (stride < 1) stride = 1;
     while (stride > 1 && std::__gcd(stride, nchunks) != 1) stride--;
-    static int occ256 = 0, occ512 = 0;
-    if (!occ256) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ256, k_ransac_validate<256>, 256, 0));
-    if (!occ512) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ512, k_ransac_validate<512>, 512, 0));
+    int &occ256 = ctx->occ_val256, &occ512 = ctx->occ_val512;  // per context (one thread at a time), hence per device
+    if (!occ256) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ256, k_ransac_validate<256, true>, 256, 0));
+    if (!occ512) PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ512, k_ransac_validate<512, true>, 512, 0));
     const int per_sm = vthreads == 1024 ? 1 : (vthreads == 512 ? (occ512 > 0 ? occ512 : 2) : (occ256 > 0 ? occ256 : 4));
     const int vblocks = (int)std::min<long long>(count, (long long)ctx->sm_count * per_sm);
     const size_t pend_idx = ctx->pending.size();
