@@ -91,6 +91,18 @@ struct RansacWork {
     bool use_lists;
 };
 
+// One RANSAC wave in two steps (pcr_ransac.cu): generation does not depend on the best result so far, validation does — so the
+// next wave can be generated (on another stream) while this one is validated and, on several GPUs, exchanged.
+struct Survivor;
+struct WaveWork {
+    Survivor *surv = nullptr;          // set by the caller: use these buffers; nullptr: wave_generate takes arena scratch
+    unsigned char *hdr = nullptr;      // 4 counters (survivors, records, ticket, -) + the record buffer (cap records)
+    int *bucket_best = nullptr;
+    long long hyp_begin = 0, count = 0;
+    int cap = 0;
+};
+size_t pcr_wave_survivor_bytes(long long count);
+
 struct pcr_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;

@@ -34,6 +34,11 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
                          double max_dist, double edge_sim, long long hyp_begin, long long hyp_end, u64 seed, long long best_cnt,
                          long long best_sumq, pcr_hyp_record *recs_host, int cap, int *n_recs_host, long long *n_surv_host);
 int pcr_corr_check_impl(pcr_ctx *ctx, const int *corr, int c, int ms, int mt);
+int pcr_wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, double max_dist, double edge_sim,
+                      long long hyp_begin, long long hyp_end, u64 seed, int cap, WaveWork *ww);
+int pcr_wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt, const int *corr, int c,
+                      double max_dist, const WaveWork &ww, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
+                      int *n_recs_host, long long *n_surv_host);
 int pcr_align_device_impl(pcr_ctx *ctx, const float4 *src, int ns, const float4 *tgt, int nt, const pcr_align_params *p,
                           pcr_align_result *res);
 
@@ -90,6 +95,7 @@ struct DistState {
     void *host_buf = nullptr;  // pinned mirror
     size_t host_bytes = 0;
     std::vector<pcr_ctx *> workers;  // pcr_align_batch: extra contexts of this rank (worker 0 is the caller's context)
+    cudaStream_t spec_stream = nullptr;  // pcr_ransac_multi: the next wave's hypotheses are generated here
 };
 
 DistState *dist_of(pcr_ctx *ctx) {
@@ -247,22 +253,100 @@ int pcr_ransac_multi(pcr_ctx *ctx, const float *src_, int ms, const float *tgt_,
     const size_t blk_words = 2 + (size_t)FIXED_CAP * REC_WORDS;
     std::vector<pcr_hyp_record> recs, merged;
     std::vector<long long> sendb(blk_words), recvb(blk_words * (size_t)world);
+    // The hypotheses of wave k + 1 are generated on a second stream while wave k is validated, read back, exchanged and
+    // replayed (generation needs nothing of that; it is ~20 % of a run's GPU work): the GPU no longer idles while the ranks
+    // wait for the slowest of them in the all-gather.  Two survivor buffers, sized for the largest slice of the schedule,
+    // alternate.  PCR_DIST_SPECULATE=0: one wave after the other.
+    static const bool spec_on = !(getenv("PCR_DIST_SPECULATE") && atoi(getenv("PCR_DIST_SPECULATE")) == 0);
+    if (spec_on && !d->spec_stream && cudaStreamCreateWithFlags(&d->spec_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        d->spec_stream = nullptr;
+    }
+    const bool speculate = spec_on && d->spec_stream != nullptr;
+    constexpr int CAP0 = 4096;
+    WaveWork bufs[2];
+    if (speculate) {
+        int64_t b = 0, wv = wave, max_slice = 1;
+        while (b < max_iter) {
+            const int64_t e = std::min<int64_t>(max_iter, b + wv), nn = e - b;
+            max_slice = std::max<int64_t>(max_slice, (nn + world - 1) / world + 1);
+            b = e;
+            if (wv < max_wave * world) wv *= growth;
+        }
+        for (int k = 0; k < 2; k++) {
+            bufs[k].surv = (Survivor *)arena<unsigned char>(ctx, pcr_wave_survivor_bytes(max_slice));
+            bufs[k].hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)CAP0);
+            bufs[k].bucket_best = arena<int>(ctx, 64);
+            if (!bufs[k].surv || !bufs[k].hdr || !bufs[k].bucket_best) return PCR_ERR_OOM;
+        }
+    }
+    cudaEvent_t spec_done = nullptr;  // non-null: bufs[cur] holds the generated survivors of the wave that starts at `begin`
+    int cur = 0;
+    struct SpecGuard {  // a speculated wave that is never used still runs on this call's arena: wait for it on every path
+        cudaEvent_t *ev;
+        cudaStream_t s;
+        ~SpecGuard() {
+            if (*ev) {
+                cudaEventDestroy(*ev);
+                cudaStreamSynchronize(s);
+            }
+        }
+    } spec_guard{&spec_done, d->spec_stream};
     while (begin < max_iter && begin < res->est_k) {
         const int64_t end = std::min<int64_t>(max_iter, begin + wave);
         const int64_t n = end - begin;
         const int64_t lo = begin + n * rank / world, hi = begin + n * (rank + 1) / world;
+        const int64_t wave_next = wave < max_wave * world ? wave * growth : wave;
         int nrec = 0;
         long long nsurv = 0;
         if (hi > lo) {
-            int cap = 4096;
-            for (;;) {
-                recs.resize((size_t)cap);
-                const int rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, lo, hi, seed, res->inlier_count,
-                                                    res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
-                if (rc == PCR_OK) break;
-                if (rc == PCR_ERR_INVALID && cap < (1 << 24) && (int64_t)cap < hi - lo) { cap *= 16; continue; }
-                return rc;
+            int cap = CAP0;
+            recs.resize((size_t)cap);
+            int rc;
+            if (speculate) {
+                WaveWork &ww = bufs[cur];
+                if (spec_done) {  // generated during the previous wave
+                    PCR_CUDA(cudaStreamWaitEvent(ctx->stream, spec_done, 0));
+                    PCR_CUDA(cudaEventDestroy(spec_done));
+                    spec_done = nullptr;
+                    rc = PCR_OK;
+                } else {
+                    rc = pcr_wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, lo, hi, seed, cap, &ww);
+                }
+                // this rank's slice of the next wave, on the other stream and in the other buffer
+                const int64_t end2 = std::min<int64_t>(max_iter, end + wave_next), n2 = end2 - end;
+                const int64_t lo2 = end + n2 * rank / world, hi2 = end + n2 * (rank + 1) / world;
+                if (rc == PCR_OK && hi2 > lo2) {
+                    cudaEvent_t in_ready;
+                    PCR_CUDA(cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming));
+                    PCR_CUDA(cudaEventRecord(in_ready, ctx->stream));  // inputs complete; the other buffer's last reader (wave k - 1) is done
+                    PCR_CUDA(cudaStreamWaitEvent(d->spec_stream, in_ready, 0));
+                    PCR_CUDA(cudaEventDestroy(in_ready));
+                    cudaStream_t keep = ctx->stream;
+                    ctx->stream = d->spec_stream;
+                    const int rcs = pcr_wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, lo2, hi2, seed, CAP0, &bufs[cur ^ 1]);
+                    ctx->stream = keep;
+                    if (rcs == PCR_OK && cudaEventCreateWithFlags(&spec_done, cudaEventDisableTiming) == cudaSuccess) {
+                        cudaEventRecord(spec_done, d->spec_stream);
+                    } else {
+                        spec_done = nullptr;
+                        cudaStreamSynchronize(d->spec_stream);
+                    }
+                }
+                if (rc == PCR_OK)
+                    rc = pcr_wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, ww, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
+            } else {
+                rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, lo, hi, seed, res->inlier_count,
+                                          res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
             }
+            // a slice whose records did not fit: generated and validated again with a larger record buffer (arena scratch)
+            while (rc == PCR_ERR_INVALID && cap < (1 << 24) && (int64_t)cap < hi - lo) {
+                cap *= 16;
+                recs.resize((size_t)cap);
+                rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, lo, hi, seed, res->inlier_count,
+                                          res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
+            }
+            if (rc != PCR_OK) return rc;
         }
         // chain of prefix maxima of this rank's slice (records are sorted by hypothesis index)
         std::vector<pcr_hyp_record> chain;
@@ -313,7 +397,8 @@ int pcr_ransac_multi(pcr_ctx *ctx, const float *src_, int ms, const float *tgt_,
         waves++;
         begin = end;
         if (stop) break;
-        if (wave < max_wave * world) wave *= growth;
+        wave = wave_next;
+        cur ^= 1;
     }
     res->survivors = survivors;
     res->k_d = w.k_d;

@@ -551,31 +551,29 @@ int pcr_ransac_session_begin_impl(pcr_ctx *ctx, const float4 *src, int ms, const
     return PCR_OK;
 }
 
-// One wave in two steps so that the NEXT wave's hypotheses can be generated (on another stream) while this wave's
-// survivors are validated: generation does not depend on the best result so far, validation does.
-struct WaveWork {
-    Survivor *surv;
-    unsigned char *hdr;       // 4 counters (survivors, records, ticket, -) + the record buffer
-    int *bucket_best;
-    long long hyp_begin, count;
-    int cap;
-};
+size_t pcr_wave_survivor_bytes(long long count) { return sizeof(Survivor) * (size_t)count; }
 
 // step 1 (on ctx->stream, scratch from the arena — the caller releases it): survivors of [hyp_begin, hyp_end)
-static int wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, double max_dist,
+int pcr_wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, const int *corr, int c, double max_dist,
                          double edge_sim, long long hyp_begin, long long hyp_end, u64 seed, int cap, WaveWork *ww) {
     const long long count = hyp_end - hyp_begin;
     ww->hyp_begin = hyp_begin;
     ww->count = count;
     ww->cap = cap;
     if (count > (1LL << 30)) return pcr_fail(ctx, PCR_ERR_INVALID, "wave too large");
-    PCR_ALLOC(surv, Survivor, (size_t)count);
+    // the caller's buffers (ww->surv set: room for `count` survivors, 16 + cap records, VAL_BUCKETS ints), else arena scratch;
     // counters and records share one buffer so that the common case (few records) needs ONE D2H copy + sync
-    unsigned char *hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)cap);
-    if (!hdr) return PCR_ERR_OOM;
+    Survivor *surv = ww->surv;
+    unsigned char *hdr = ww->hdr;
+    int *bucket_best = ww->bucket_best;
+    if (!surv) {
+        surv = arena<Survivor>(ctx, (size_t)count);
+        hdr = arena<unsigned char>(ctx, 16 + sizeof(pcr_hyp_record) * (size_t)cap);
+        bucket_best = arena<int>(ctx, VAL_BUCKETS);
+        if (!surv || !hdr || !bucket_best) return PCR_ERR_OOM;
+    }
     unsigned int *counters = (unsigned int *)hdr;
     PCR_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), ctx->stream));
-    PCR_ALLOC(bucket_best, int, VAL_BUCKETS);
     PCR_CUDA(cudaMemsetAsync(bucket_best, 0xff, VAL_BUCKETS * sizeof(int), ctx->stream));
     {
         KScope ks(ctx, KC_RANSAC_GENERATE, 120.0 * (double)count);
@@ -591,7 +589,7 @@ static int wave_generate(pcr_ctx *ctx, const float4 *src, const float4 *tgt, con
 }
 
 // step 2: validation against (best_cnt, best_sumq), records to the host (sorted by hypothesis)
-static int wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt, const int *corr, int c,
+int pcr_wave_validate(pcr_ctx *ctx, const RansacWork &w, const float4 *src, int ms, const float4 *tgt, const int *corr, int c,
                          double max_dist, const WaveWork &ww, long long best_cnt, long long best_sumq, pcr_hyp_record *recs_host,
                          int *n_recs_host, long long *n_surv_host) {
     const long long count = ww.count, hyp_begin = ww.hyp_begin, hyp_end = ww.hyp_begin + ww.count;
@@ -693,8 +691,8 @@ int pcr_ransac_wave_impl(pcr_ctx *ctx, const RansacWork &w, const float4 *src, i
     if (hyp_end - hyp_begin <= 0) return PCR_OK;
     const size_t mark_block = ctx->cur_block, mark_off = ctx->cur_off;  // wave scratch is released on return
     WaveWork ww;
-    int rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, hyp_begin, hyp_end, seed, cap, &ww);
-    if (rc == PCR_OK) rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, ww, best_cnt, best_sumq, recs_host, n_recs_host, n_surv_host);
+    int rc = pcr_wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, hyp_begin, hyp_end, seed, cap, &ww);
+    if (rc == PCR_OK) rc = pcr_wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, ww, best_cnt, best_sumq, recs_host, n_recs_host, n_surv_host);
     ctx->cur_block = mark_block;
     ctx->cur_off = mark_off;
     return rc;
@@ -784,7 +782,7 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
         int rc;
         if (wave_idx == 0 && speculate && ctx->aux2_stream && ctx->aux2_stream != ctx->stream && end < max_iter) {
             WaveWork w0;
-            rc = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, begin, end, seed, cap, &w0);
+            rc = pcr_wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, begin, end, seed, cap, &w0);
             if (rc == PCR_OK) {
                 cudaEvent_t in_ready;
                 cudaEventCreateWithFlags(&in_ready, cudaEventDisableTiming);
@@ -793,19 +791,19 @@ int pcr_ransac_impl(pcr_ctx *ctx, const float4 *src, int ms, const float4 *tgt, 
                 cudaEventDestroy(in_ready);
                 cudaStream_t keep = ctx->stream;
                 ctx->stream = ctx->aux2_stream;
-                const int rcs = wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, end, std::min<int64_t>(max_iter, end + next_wave), seed,
+                const int rcs = pcr_wave_generate(ctx, src, tgt, corr, c, max_dist, edge_sim, end, std::min<int64_t>(max_iter, end + next_wave), seed,
                                               4096, &spec);
                 ctx->stream = keep;
                 if (rcs == PCR_OK && cudaEventCreateWithFlags(&spec_done, cudaEventDisableTiming) == cudaSuccess)
                     cudaEventRecord(spec_done, ctx->aux2_stream);
                 else cudaStreamSynchronize(ctx->aux2_stream);  // no speculation: the wave is generated again in its turn
-                rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, w0, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
+                rc = pcr_wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, w0, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
             }
         } else if (wave_idx == 1 && spec_done) {
             cudaStreamWaitEvent(ctx->stream, spec_done, 0);
             cudaEventDestroy(spec_done);
             spec_done = nullptr;
-            rc = wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, spec, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
+            rc = pcr_wave_validate(ctx, w, src, ms, tgt, corr, c, max_dist, spec, res->inlier_count, res->sum_d2_fixed, recs.data(), &nrec, &nsurv);
         } else {
             rc = pcr_ransac_wave_impl(ctx, w, src, ms, tgt, corr, c, max_dist, edge_sim, begin, end, seed, res->inlier_count,
                                       res->sum_d2_fixed, recs.data(), cap, &nrec, &nsurv);
