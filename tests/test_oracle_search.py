@@ -50,6 +50,27 @@ def test_voxel_downsample(orc, n, voxel):
     assert orc.voxel_downsample(np.zeros((0, 3), np.float32), 0.3).shape == (0, 3)
 
 
+def test_voxel_downsample_on_grids_far_beyond_a_dense_table(orc):
+    """The oracle sorts 64-bit voxel keys, so the extent / voxel ratio is unbounded (Open3D hashes the index): two dense
+    clusters 10^5 units apart plus isolated points, 10^15 voxel ids.  Checked against the NumPy restatement (np.unique on
+    the same keys, fp64 means) — this is the case the device's sorted-key path is compared with on the GPU."""
+    rng = np.random.default_rng(11)
+    a = cloud(1500, 7) * 2.0
+    b = a[:700] + np.array([1e5, -3e4, 2e4], np.float32)
+    lone = rng.uniform(-5e4, 5e4, (300, 3)).astype(np.float32)
+    pts = np.concatenate([a, b, lone]).astype(np.float32)
+    voxel = 0.3
+    ext = pts.max(0).astype(np.float64) - pts.min(0)
+    assert np.prod(np.floor(ext / voxel) + 1) > 1e15
+    out = orc.voxel_downsample(pts, voxel)
+    ref = np_ref.voxel_downsample(pts, voxel)
+    assert out.shape == ref.shape and len(out) < len(pts)
+    # means of fp32 coordinates of magnitude 1e5: the fixed-point sums agree with fp64 means to half an fp32 ulp there
+    assert np.allclose(out, ref, rtol=0, atol=4e-3) and np.allclose(out[np.abs(ref).max(1) < 10], ref[np.abs(ref).max(1) < 10], rtol=0, atol=1e-6)
+    with pytest.raises(ValueError):  # a dimension beyond int32
+        orc.voxel_downsample(pts, 1e-6)
+
+
 def test_voxel_is_order_independent(orc):
     pts = cloud(3000, 5)
     a = orc.voxel_downsample(pts, 0.2)
